@@ -1,0 +1,130 @@
+/* hitsir_b200 -- C ABI of the B200-native HiT-SIR-pro forward pass.
+ *
+ * Drop-in boundary for ONE path of CoderLinxin/Single-Image-Super-Resolution-Application:
+ * `HiT_SIR.forward` (reference: models/hit_sir_pro.py:1304-1344, constructed at
+ * models/hit_sir_pro.py:1091-1265).  The reference has no FFI of its own (it is pure PyTorch);
+ * every entry point below therefore names the reference *Python* interface it stands in for, and
+ * INTEGRATION.md shows the ctypes binding a maintainer adds (it is what
+ * `hitsir_b200.HiT_SIR` uses).
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every function returns 0 on
+ * success and a non-zero status otherwise, with a human-readable message available from
+ * hitsir_last_error() (thread-local).  The library never synchronises the device, never
+ * changes the current device and launches everything on the caller's stream.  It owns only the
+ * packed weights tied to a handle; inputs, outputs and the workspace belong to the caller.
+ * There is no CPU path: without an sm_100 device every compute entry point fails.
+ */
+#ifndef HITSIR_B200_H_
+#define HITSIR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define HITSIR_API __attribute__((visibility("default")))
+#else
+#define HITSIR_API
+#endif
+
+#define HITSIR_MAX_LAYERS 16
+#define HITSIR_MAX_DEPTH 16
+
+/* status codes */
+enum {
+  HITSIR_OK = 0,
+  HITSIR_ERR_CUDA = 1,           /* a CUDA call failed (message has the details)                     */
+  HITSIR_ERR_INVALID = 2,        /* bad argument / unknown parameter name / wrong element count        */
+  HITSIR_ERR_UNSUPPORTED = 3,    /* legal reference configuration this build does not implement        */
+  HITSIR_ERR_INPUT_TOO_SMALL = 4,/* reflect padding needs pad < dim (RuntimeError at hit_sir_pro.py:672) */
+  HITSIR_ERR_WEIGHTS = 5,        /* forward before all parameters were provided / finalized            */
+  HITSIR_ERR_WORKSPACE = 6       /* workspace too small or misaligned                                  */
+};
+
+/* upsampler selector: reference constructor argument `upsampler` (hit_sir_pro.py:1116, 1235-1262) */
+enum {
+  HITSIR_UP_NONE = 0,                /* upsampler=None / '' : x + conv_last(res)   (:1335-1340) */
+  HITSIR_UP_PIXELSHUFFLE = 1,        /* 'pixelshuffle'                            (:1313-1319) */
+  HITSIR_UP_PIXELSHUFFLEDIRECT = 2,  /* 'pixelshuffledirect'                      (:1320-1325) */
+  HITSIR_UP_NEAREST_CONV = 3         /* 'nearest+conv' (x4 only, assert at :1248) (:1326-1334) */
+};
+
+/* Mirrors the constructor arguments of HiT_SIR.__init__ (hit_sir_pro.py:1091-1120) that change
+ * the forward pass.  Arguments with no effect at inference (img_size, patch_size, drop rates at
+ * eval, use_checkpoint, norm_layer=LayerNorm) are handled by the Python mirror. */
+typedef struct HitsirConfig {
+  int32_t is_mult_size_conv_feat_extract; /* "mulsizeconvextract" */
+  int32_t is_channel_spatial_attn;        /* "casa"               */
+  int32_t is_fusion;
+  int32_t in_chans;                       /* 3 (RGB mean subtracted, :1126-1131) or 1 */
+  int32_t embed_dim;                      /* 180 in this build */
+  int32_t num_layers;                     /* len(depths) */
+  int32_t depths[HITSIR_MAX_LAYERS];
+  int32_t num_heads[HITSIR_MAX_LAYERS];   /* 6 in this build */
+  int32_t base_win_size[2];               /* square, <= 8 */
+  float mlp_ratio;                        /* 2.0 in this build */
+  int32_t upscale;
+  float img_range;
+  int32_t upsampler;                      /* HITSIR_UP_* */
+  int32_t num_ratios;
+  float hier_win_ratios[HITSIR_MAX_DEPTH];
+} HitsirConfig;
+
+typedef struct HitsirHandle HitsirHandle;
+
+/* HiT_SIR.__init__ (hit_sir_pro.py:1091).  Binds the handle to the CURRENT CUDA device. */
+HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out);
+HITSIR_API void hitsir_destroy(HitsirHandle* h);
+
+/* Names/sizes of the parameters the handle expects == the reference state_dict keys
+ * (nn.Module.state_dict(), used by experiment.py:223,260).  hitsir_param_name returns NULL past the end. */
+HITSIR_API int hitsir_num_params(const HitsirHandle* h);
+HITSIR_API const char* hitsir_param_name(const HitsirHandle* h, int index);
+HITSIR_API int64_t hitsir_param_numel(const HitsirHandle* h, int index);
+
+/* nn.Module.load_state_dict(): provide one fp32 tensor by its state_dict key.  `data` may be a
+ * device or a host pointer (copied with cudaMemcpyDefault on `stream`); contiguous, `numel` floats. */
+HITSIR_API int hitsir_set_param(HitsirHandle* h, const char* name, const float* data, int64_t numel, void* stream);
+/* Pack weights (bf16 K-major operands, padded) and precompute the pooled relative-position bias
+ * tables (hit_sir_pro.py:477-503 hoisted out of the forward).  Call after all parameters are set
+ * and again whenever any of them changed. */
+HITSIR_API int hitsir_finalize_weights(HitsirHandle* h, void* stream);
+
+/* Scratch memory needed by hitsir_forward for a (B,H,W) input; 256-byte aligned base required. */
+HITSIR_API int hitsir_workspace_bytes(const HitsirHandle* h, int B, int H, int W, size_t* bytes);
+
+/* HiT_SIR.forward (hit_sir_pro.py:1304-1344): x (B,in_chans,H,W) fp32 NCHW on the device ->
+ * y (B,in_chans,H*upscale,W*upscale) fp32 NCHW on the device.  Asynchronous on `stream`. */
+HITSIR_API int hitsir_forward(HitsirHandle* h, const float* x, float* y, int B, int H, int W,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same call with HOST buffers (pinned recommended): copies x host->device, runs the forward,
+ * copies y device->host, all on `stream`; `dev_x`/`dev_y` are caller-provided device staging
+ * buffers of B*C*H*W and B*C*sH*sW floats.  Returns after enqueueing; the caller synchronises. */
+HITSIR_API int hitsir_forward_host(HitsirHandle* h, const float* host_x, float* host_y, int B, int H, int W,
+                        float* dev_x, float* dev_y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Test hook standing in for PyTorch forward hooks on reference sub-modules: the next
+ * hitsir_forward copies the named intermediate activation (fp32, NHWC, real channels only) into
+ * `dst` (device) and, when `stop` != 0, returns right after producing it.  Names: "shallow",
+ * "embed", "block<i>.<j>.qkv", "block<i>.<j>.scc", "block<i>.<j>.attn", "block<i>.<j>",
+ * "layer<i>", "norm", "conv_after_body", "fused", "conv_before_upsample", "up1", "up2", "hr".
+ * Pass name = NULL to clear. */
+HITSIR_API int hitsir_set_tap(HitsirHandle* h, const char* name, float* dst, int64_t dst_floats, int stop);
+
+/* Number of kernels the last hitsir_forward launched (bench.py's gpu_launches). */
+HITSIR_API int64_t hitsir_last_launch_count(const HitsirHandle* h);
+
+/* "umma" (tcgen05 path, default) or "simt" (cross-check kernels); also via env HITSIR_GEMM. */
+HITSIR_API int hitsir_set_gemm_backend(HitsirHandle* h, const char* backend);
+
+HITSIR_API const char* hitsir_last_error(void);
+HITSIR_API const char* hitsir_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HITSIR_B200_H_ */

@@ -1,0 +1,894 @@
+// hitsir_b200 engine: parameter registry (reference state_dict keys), weight packing, workspace
+// layout and the forward-pass orchestration of HiT_SIR.forward
+// (/root/reference/models/hit_sir_pro.py:1304-1344) behind the C ABI of include/hitsir_b200.h.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/hitsir_b200.h"
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace hitsir {
+
+static thread_local char g_err[2048] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+struct ParamSpec {
+  std::string name;
+  int64_t numel;
+  size_t offset;   // floats into the master arena
+  bool set;
+};
+
+// one packed dense operand (bf16 [Npad][K]) + fp32 bias [Npad] + its TMA descriptor
+struct GemmW {
+  bf16* w = nullptr;
+  float* b = nullptr;
+  int Npad = 0, K = 0, BN = 0;
+  CUtensorMap tm;
+};
+
+struct BlockW {
+  int win = 0, base = 0, r = 0;
+  const float *g1, *b1, *g2, *b2;
+  CasaW casa;
+  float *casa_w1 = nullptr, *casa_w2 = nullptr;
+  SccW scc;
+  float* bias_tbl = nullptr;
+  GemmW proj, fc1, fc2;
+  float *dw_w = nullptr, *dw_b = nullptr;
+};
+
+struct UaPack {
+  UaW small;
+  GemmW conv_last;
+};
+
+struct Tap {
+  std::string name;
+  float* dst = nullptr;
+  int64_t floats = 0;
+  int stop = 0;
+};
+
+}  // namespace hitsir
+
+using namespace hitsir;
+
+struct HitsirHandle {
+  HitsirConfig cfg;
+  int device = 0;
+  int num_sms = 148;
+  bool simt = false;
+  std::vector<ParamSpec> params;
+  std::map<std::string, int> index;
+  float* arena = nullptr;      // device fp32 master copy of every parameter
+  size_t arena_floats = 0;
+  bool finalized = false;
+  std::vector<void*> owned;    // packed buffers
+  // packed weights
+  GemmW first, first_last;     // conv_first (im2col GEMM) and its 1x1 conv_last (ms only)
+  int first_f = 3, first_kp = 64;
+  std::vector<std::vector<BlockW>> blocks;
+  std::vector<GemmW> layer_conv;
+  GemmW conv_after_body;
+  UaPack ua[3];
+  GemmW conv_before_upsample, conv_up1, conv_up2, conv_hr, conv_last;
+  std::vector<GemmW> upsample;   // pixelshuffle stages / pixelshuffledirect
+  float mean[4] = {0, 0, 0, 0};
+  // per-forward state
+  Tap tap;
+  int64_t launches = 0;
+};
+
+namespace {
+
+const int kNumFeat = 64;
+
+int win_of(const HitsirConfig& c, int j) { return (int)(c.base_win_size[0] * c.hier_win_ratios[j]); }
+
+void add_param(HitsirHandle* h, const std::string& name, int64_t numel) {
+  ParamSpec p{name, numel, h->arena_floats, false};
+  h->arena_floats += (size_t)((numel + 3) / 4 * 4);   // keep every tensor 16-byte aligned
+  h->index[name] = (int)h->params.size();
+  h->params.push_back(p);
+}
+void add_wb(HitsirHandle* h, const std::string& prefix, int64_t wn, int64_t bn) {
+  add_param(h, prefix + ".weight", wn);
+  add_param(h, prefix + ".bias", bn);
+}
+
+void build_param_list(HitsirHandle* h) {
+  const HitsirConfig& c = h->cfg;
+  const int C = c.embed_dim, ic = c.in_chans;
+  if (c.is_mult_size_conv_feat_extract) {
+    add_wb(h, "conv_first.conv3", (int64_t)C * ic * 9, C);
+    add_wb(h, "conv_first.conv5", (int64_t)C * ic * 25, C);
+    add_wb(h, "conv_first.conv7", (int64_t)C * ic * 49, C);
+    add_wb(h, "conv_first.conv9", (int64_t)C * ic * 81, C);
+    add_wb(h, "conv_first.conv_x", (int64_t)C * 3, C);          // nn.Conv2d(3, ...) hard-coded (:59)
+    add_wb(h, "conv_first.norm", C, C);                         // registered but never applied (:62)
+    add_wb(h, "conv_first.conv_last", (int64_t)C * 4 * C, C);
+  } else {
+    add_wb(h, "conv_first", (int64_t)C * ic * 9, C);
+  }
+  if (c.is_fusion) {
+    for (int u = 1; u <= 3; ++u) {
+      const std::string p = "fusion.union_attention" + std::to_string(u);
+      add_wb(h, p + ".conv1", 18, 1);
+      add_wb(h, p + ".conv2", 18, 1);
+      add_wb(h, p + ".conv3", 18, 1);
+      add_wb(h, p + ".conv_last", (int64_t)C * C * 9, C);
+    }
+  }
+  add_wb(h, "patch_embed.norm", C, C);
+  const int hd = C / (2 * c.num_heads[0]);
+  const int pos_dim = (C / 4) / 4;
+  const int hidden = (int)(C * c.mlp_ratio);
+  for (int i = 0; i < c.num_layers; ++i) {
+    for (int j = 0; j < c.depths[i]; ++j) {
+      const std::string p = "layers." + std::to_string(i) + ".residual_group.blocks." + std::to_string(j);
+      const int w = win_of(c, j), base = w < c.base_win_size[0] ? w : c.base_win_size[0], r = w / base;
+      add_wb(h, p + ".norm1", C, C);
+      if (c.is_channel_spatial_attn) {
+        add_wb(h, p + ".correlation.qkv.linear1", (int64_t)C * 9, C);
+        add_wb(h, p + ".correlation.qkv.linear2", (int64_t)C * 9, C);
+        add_wb(h, p + ".correlation.qkv.linear1_first", (int64_t)(C / 10) * C, C / 10);
+        add_wb(h, p + ".correlation.qkv.linear1_second", (int64_t)C * (C / 10), C);
+        add_wb(h, p + ".correlation.qkv.linear2_first", (int64_t)(C / 10) * C, C / 10);
+        add_wb(h, p + ".correlation.qkv.linear2_second", (int64_t)C * (C / 10), C);
+      }
+      add_wb(h, p + ".correlation.proj", (int64_t)C * C, C);
+      add_wb(h, p + ".correlation.spatial_linear", (int64_t)r * r, 1);
+      add_wb(h, p + ".correlation.k_generate1", (int64_t)hd * hd, hd);
+      add_wb(h, p + ".correlation.k_generate2", (int64_t)hd * hd, hd);
+      add_wb(h, p + ".correlation.pos.pos_proj", (int64_t)pos_dim * 2, pos_dim);
+      add_wb(h, p + ".correlation.pos.pos1.0", pos_dim, pos_dim);
+      add_wb(h, p + ".correlation.pos.pos1.2", (int64_t)pos_dim * pos_dim, pos_dim);
+      add_wb(h, p + ".correlation.pos.pos2.0", pos_dim, pos_dim);
+      add_wb(h, p + ".correlation.pos.pos2.2", (int64_t)pos_dim * pos_dim, pos_dim);
+      add_wb(h, p + ".correlation.pos.pos3.0", pos_dim, pos_dim);
+      add_wb(h, p + ".correlation.pos.pos3.2", (int64_t)c.num_heads[i] * pos_dim, c.num_heads[i]);
+      add_wb(h, p + ".norm2", C, C);
+      add_wb(h, p + ".mlp.fc1", (int64_t)hidden * C, hidden);
+      add_wb(h, p + ".mlp.dwconv.depthwise_conv.0", (int64_t)hidden * 25, hidden);
+      add_wb(h, p + ".mlp.fc2", (int64_t)C * hidden, C);
+    }
+    add_wb(h, "layers." + std::to_string(i) + ".conv", (int64_t)C * C * 9, C);
+  }
+  add_wb(h, "norm", C, C);
+  add_wb(h, "conv_after_body", (int64_t)C * C * 9, C);
+  const int s = c.upscale;
+  switch (c.upsampler) {
+    case HITSIR_UP_PIXELSHUFFLE:
+      add_wb(h, "conv_before_upsample.0", (int64_t)kNumFeat * C * 9, kNumFeat);
+      if ((s & (s - 1)) == 0) {
+        int n = 0;
+        for (int t = s; t > 1; t >>= 1) ++n;
+        for (int k = 0; k < n; ++k) add_wb(h, "upsample." + std::to_string(2 * k), (int64_t)4 * kNumFeat * kNumFeat * 9, 4 * kNumFeat);
+      } else {
+        add_wb(h, "upsample.0", (int64_t)9 * kNumFeat * kNumFeat * 9, 9 * kNumFeat);
+      }
+      add_wb(h, "conv_last", (int64_t)ic * kNumFeat * 9, ic);
+      break;
+    case HITSIR_UP_PIXELSHUFFLEDIRECT:
+      add_wb(h, "upsample.0", (int64_t)s * s * ic * C * 9, s * s * ic);
+      break;
+    case HITSIR_UP_NEAREST_CONV:
+      add_wb(h, "conv_before_upsample.0", (int64_t)kNumFeat * C * 9, kNumFeat);
+      add_wb(h, "conv_up1", (int64_t)kNumFeat * kNumFeat * 9, kNumFeat);
+      add_wb(h, "conv_up2", (int64_t)kNumFeat * kNumFeat * 9, kNumFeat);
+      add_wb(h, "conv_hr", (int64_t)kNumFeat * kNumFeat * 9, kNumFeat);
+      add_wb(h, "conv_last", (int64_t)ic * kNumFeat * 9, ic);
+      break;
+    default:
+      add_wb(h, "conv_last", (int64_t)ic * C * 9, ic);
+      break;
+  }
+}
+
+int validate_config(const HitsirConfig& c) {
+  if (c.embed_dim != kC) { set_error("unsupported embed_dim %d: this build implements HiT-SIR-pro (embed_dim=180)", c.embed_dim); return HITSIR_ERR_UNSUPPORTED; }
+  if (c.in_chans != 3 && c.in_chans != 1) { set_error("in_chans must be 1 or 3, got %d", c.in_chans); return HITSIR_ERR_UNSUPPORTED; }
+  if (c.is_mult_size_conv_feat_extract && c.in_chans != 3) { set_error("MultipleSizeConvExtract needs in_chans == 3 (conv_x is Conv2d(3,..), hit_sir_pro.py:59)"); return HITSIR_ERR_UNSUPPORTED; }
+  if (c.num_layers < 1 || c.num_layers > HITSIR_MAX_LAYERS) { set_error("num_layers %d out of range", c.num_layers); return HITSIR_ERR_INVALID; }
+  if (c.mlp_ratio != 2.0f) { set_error("unsupported mlp_ratio %f (this build: 2.0)", c.mlp_ratio); return HITSIR_ERR_UNSUPPORTED; }
+  if (c.base_win_size[0] != c.base_win_size[1] || c.base_win_size[0] < 1 || c.base_win_size[0] > 8) {
+    set_error("unsupported base_win_size (%d,%d): square windows with base <= 8 only", c.base_win_size[0], c.base_win_size[1]);
+    return HITSIR_ERR_UNSUPPORTED;
+  }
+  for (int i = 0; i < c.num_layers; ++i) {
+    if (c.num_heads[i] != kHeads) { set_error("unsupported num_heads[%d]=%d (this build: 6)", i, c.num_heads[i]); return HITSIR_ERR_UNSUPPORTED; }
+    if (c.depths[i] < 1 || c.depths[i] > c.num_ratios || c.depths[i] > HITSIR_MAX_DEPTH) {
+      set_error("depths[%d]=%d needs that many hier_win_ratios (have %d)", i, c.depths[i], c.num_ratios);
+      return HITSIR_ERR_INVALID;
+    }
+    for (int j = 0; j < c.depths[i]; ++j) {
+      const int w = win_of(c, j), bs = c.base_win_size[0];
+      if (w < 1) { set_error("window %d of block %d is empty", w, j); return HITSIR_ERR_INVALID; }
+      // reference assertion, hit_sir_pro.py:647-649
+      if (w > bs && w % bs != 0) { set_error("please ensure the window size is smaller than or divisible by the base window size"); return HITSIR_ERR_INVALID; }
+      if (w > 64) { set_error("window %d > 64 not supported by this build", w); return HITSIR_ERR_UNSUPPORTED; }
+    }
+  }
+  if (c.upsampler == HITSIR_UP_NEAREST_CONV && c.upscale != 4) { set_error("only support x4 now."); return HITSIR_ERR_INVALID; }   // (:1248)
+  if (c.upsampler == HITSIR_UP_PIXELSHUFFLE) {
+    const int s = c.upscale;
+    if (!((s & (s - 1)) == 0 || s == 3) || s < 1) { set_error("scale %d is not supported. Supported scales: 2^n and 3.", s); return HITSIR_ERR_INVALID; }   // (:1042)
+  }
+  if (c.upsampler == HITSIR_UP_PIXELSHUFFLEDIRECT && (c.upscale < 1 || c.upscale * c.upscale * c.in_chans > 256)) {
+    set_error("pixelshuffledirect upscale %d not supported", c.upscale); return HITSIR_ERR_UNSUPPORTED;
+  }
+  if (c.upsampler == HITSIR_UP_NONE && c.upscale != 1) { set_error("upsampler=None requires upscale == 1 (x + conv_last(res), hit_sir_pro.py:1340)"); return HITSIR_ERR_INVALID; }
+  return 0;
+}
+
+const float* P(const HitsirHandle* h, const std::string& name) {
+  auto it = h->index.find(name);
+  if (it == h->index.end()) return nullptr;
+  return h->arena + h->params[it->second].offset;
+}
+
+template <class T>
+int dev_alloc(HitsirHandle* h, T** p, size_t count) {
+  void* q = nullptr;
+  HITSIR_CHECK(cudaMalloc(&q, count * sizeof(T)));
+  h->owned.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return 0;
+}
+
+int pick_bn(int n) {
+  if (n <= 16) return 16;
+  if (n <= 32) return 32;
+  if (n <= 48) return 48;
+  if (n <= 64) return 64;
+  if (n % 256 == 0) return 256;
+  return 192;
+}
+
+// conv (taps=9) or linear (taps=1) weight `prefix` -> packed GEMM operand
+int make_gemm_w(HitsirHandle* h, GemmW* g, const std::string& prefix, int Co, int Ci, int taps, cudaStream_t st) {
+  const int BN = pick_bn(Co);
+  const int Npad = round_up(Co, BN), Cipad = round_up(Ci, 64);
+  g->BN = BN; g->Npad = Npad; g->K = taps * Cipad;
+  if (dev_alloc(h, &g->w, (size_t)Npad * g->K)) return 1;
+  if (dev_alloc(h, &g->b, (size_t)Npad)) return 1;
+  const float* w = P(h, prefix + ".weight");
+  const float* b = P(h, prefix + ".bias");
+  if (!w || !b) { set_error("missing parameter %s", prefix.c_str()); return 1; }
+  if (launch_pack_conv(w, b, g->w, g->b, Co, Ci, taps, Npad, Cipad, st)) return 1;
+  return make_tmap_2d(&g->tm, g->w, (uint64_t)g->K, (uint64_t)Npad, (uint64_t)g->K * 2, 64, (uint32_t)BN);
+}
+
+void free_owned(HitsirHandle* h) {
+  for (void* p : h->owned) cudaFree(p);
+  h->owned.clear();
+}
+
+int finalize(HitsirHandle* h, cudaStream_t st) {
+  for (const ParamSpec& p : h->params)
+    if (!p.set) { set_error("parameter '%s' was never provided (hitsir_set_param)", p.name.c_str()); return HITSIR_ERR_WEIGHTS; }
+  free_owned(h);
+  h->finalized = false;
+  const HitsirConfig& c = h->cfg;
+  const int C = kC, ic = c.in_chans;
+  // ---- shallow feature extraction
+  if (c.is_mult_size_conv_feat_extract) {
+    h->first_f = 9; h->first_kp = round_up(81 * ic, 64);
+    GemmW& g = h->first;
+    g.BN = 192; g.Npad = 960; g.K = h->first_kp;
+    if (dev_alloc(h, &g.w, (size_t)960 * g.K) || dev_alloc(h, &g.b, 960)) return 1;
+    if (launch_pack_msconv(P(h, "conv_first.conv3.weight"), P(h, "conv_first.conv5.weight"), P(h, "conv_first.conv7.weight"),
+                           P(h, "conv_first.conv9.weight"), P(h, "conv_first.conv_x.weight"), P(h, "conv_first.conv3.bias"),
+                           P(h, "conv_first.conv5.bias"), P(h, "conv_first.conv7.bias"), P(h, "conv_first.conv9.bias"),
+                           P(h, "conv_first.conv_x.bias"), g.w, g.b, ic, g.K, st)) return 1;
+    if (make_tmap_2d(&g.tm, g.w, (uint64_t)g.K, 960, (uint64_t)g.K * 2, 64, 192)) return 1;
+    if (make_gemm_w(h, &h->first_last, "conv_first.conv_last", C, 4 * C, 1, st)) return 1;
+  } else {
+    h->first_f = 3; h->first_kp = round_up(9 * ic, 64);
+    GemmW& g = h->first;
+    g.BN = 192; g.Npad = 192; g.K = h->first_kp;
+    if (dev_alloc(h, &g.w, (size_t)192 * g.K) || dev_alloc(h, &g.b, 192)) return 1;
+    if (launch_pack_firstconv(P(h, "conv_first.weight"), P(h, "conv_first.bias"), g.w, g.b, C, ic, 3, g.K, st)) return 1;
+    if (make_tmap_2d(&g.tm, g.w, (uint64_t)g.K, 192, (uint64_t)g.K * 2, 64, 192)) return 1;
+  }
+  // ---- blocks
+  h->blocks.assign(c.num_layers, std::vector<BlockW>());
+  h->layer_conv.assign(c.num_layers, GemmW());
+  float* tbl_scratch = nullptr;
+  if (dev_alloc(h, &tbl_scratch, (size_t)127 * 127 * kHeads)) return 1;
+  for (int i = 0; i < c.num_layers; ++i) {
+    h->blocks[i].resize(c.depths[i]);
+    for (int j = 0; j < c.depths[i]; ++j) {
+      BlockW& bw = h->blocks[i][j];
+      const std::string p = "layers." + std::to_string(i) + ".residual_group.blocks." + std::to_string(j);
+      bw.win = win_of(c, j);
+      bw.base = bw.win < c.base_win_size[0] ? bw.win : c.base_win_size[0];
+      bw.r = bw.win / bw.base;
+      bw.g1 = P(h, p + ".norm1.weight"); bw.b1 = P(h, p + ".norm1.bias");
+      bw.g2 = P(h, p + ".norm2.weight"); bw.b2 = P(h, p + ".norm2.bias");
+      if (c.is_channel_spatial_attn) {
+        const std::string q = p + ".correlation.qkv";
+        if (dev_alloc(h, &bw.casa_w1, 9 * C) || dev_alloc(h, &bw.casa_w2, 9 * C)) return 1;
+        if (launch_pack_tapmajor(P(h, q + ".linear1.weight"), bw.casa_w1, C, 9, C, st)) return 1;
+        if (launch_pack_tapmajor(P(h, q + ".linear2.weight"), bw.casa_w2, C, 9, C, st)) return 1;
+        bw.casa.w1 = bw.casa_w1; bw.casa.b1 = P(h, q + ".linear1.bias");
+        bw.casa.w2 = bw.casa_w2; bw.casa.b2 = P(h, q + ".linear2.bias");
+        bw.casa.l1f_w = P(h, q + ".linear1_first.weight"); bw.casa.l1f_b = P(h, q + ".linear1_first.bias");
+        bw.casa.l1s_w = P(h, q + ".linear1_second.weight"); bw.casa.l1s_b = P(h, q + ".linear1_second.bias");
+        bw.casa.l2f_w = P(h, q + ".linear2_first.weight"); bw.casa.l2f_b = P(h, q + ".linear2_first.bias");
+        bw.casa.l2s_w = P(h, q + ".linear2_second.weight"); bw.casa.l2s_b = P(h, q + ".linear2_second.bias");
+      }
+      const std::string s = p + ".correlation";
+      bw.scc.wk1 = P(h, s + ".k_generate1.weight"); bw.scc.bk1 = P(h, s + ".k_generate1.bias");
+      bw.scc.wk2 = P(h, s + ".k_generate2.weight"); bw.scc.bk2 = P(h, s + ".k_generate2.bias");
+      bw.scc.wsl = P(h, s + ".spatial_linear.weight");
+      bw.scc.bsl_dev = const_cast<float*>(P(h, s + ".spatial_linear.bias"));
+      PosW pw;
+      pw.proj_w = P(h, s + ".pos.pos_proj.weight"); pw.proj_b = P(h, s + ".pos.pos_proj.bias");
+      for (int k = 0; k < 3; ++k) {
+        const std::string pk = s + ".pos.pos" + std::to_string(k + 1);
+        pw.ln_w[k] = P(h, pk + ".0.weight"); pw.ln_b[k] = P(h, pk + ".0.bias");
+        pw.fc_w[k] = P(h, pk + ".2.weight"); pw.fc_b[k] = P(h, pk + ".2.bias");
+      }
+      const int L = bw.win * bw.win, Lb = bw.base * bw.base;
+      if (dev_alloc(h, &bw.bias_tbl, (size_t)kHeads * L * Lb)) return 1;
+      if (launch_pos_table(pw, bw.win, tbl_scratch, st)) return 1;
+      if (launch_pooled_bias(tbl_scratch, bw.win, bw.base, bw.bias_tbl, st)) return 1;
+      bw.scc.bias_tbl = bw.bias_tbl;
+      if (make_gemm_w(h, &bw.proj, s + ".proj", C, C, 1, st)) return 1;
+      if (make_gemm_w(h, &bw.fc1, p + ".mlp.fc1", kHid, C, 1, st)) return 1;
+      if (make_gemm_w(h, &bw.fc2, p + ".mlp.fc2", C, kHid, 1, st)) return 1;
+      if (dev_alloc(h, &bw.dw_w, 25 * kHidp) || dev_alloc(h, &bw.dw_b, kHidp)) return 1;
+      if (launch_pack_tapmajor(P(h, p + ".mlp.dwconv.depthwise_conv.0.weight"), bw.dw_w, kHid, 25, kHidp, st)) return 1;
+      if (launch_pack_tapmajor(P(h, p + ".mlp.dwconv.depthwise_conv.0.bias"), bw.dw_b, kHid, 1, kHidp, st)) return 1;
+    }
+    if (make_gemm_w(h, &h->layer_conv[i], "layers." + std::to_string(i) + ".conv", C, C, 9, st)) return 1;
+  }
+  if (make_gemm_w(h, &h->conv_after_body, "conv_after_body", C, C, 9, st)) return 1;
+  if (c.is_fusion) {
+    for (int u = 0; u < 3; ++u) {
+      const std::string p = "fusion.union_attention" + std::to_string(u + 1);
+      h->ua[u].small.c1_w = P(h, p + ".conv1.weight"); h->ua[u].small.c1_b = P(h, p + ".conv1.bias");
+      h->ua[u].small.c2_w = P(h, p + ".conv2.weight"); h->ua[u].small.c2_b = P(h, p + ".conv2.bias");
+      h->ua[u].small.c3_w = P(h, p + ".conv3.weight"); h->ua[u].small.c3_b = P(h, p + ".conv3.bias");
+      if (make_gemm_w(h, &h->ua[u].conv_last, p + ".conv_last", C, C, 9, st)) return 1;
+    }
+  }
+  h->upsample.clear();
+  const int s = c.upscale;
+  switch (c.upsampler) {
+    case HITSIR_UP_PIXELSHUFFLE: {
+      if (make_gemm_w(h, &h->conv_before_upsample, "conv_before_upsample.0", kNumFeat, C, 9, st)) return 1;
+      if ((s & (s - 1)) == 0) {
+        int n = 0;
+        for (int t = s; t > 1; t >>= 1) ++n;
+        h->upsample.resize(n);
+        for (int k = 0; k < n; ++k)
+          if (make_gemm_w(h, &h->upsample[k], "upsample." + std::to_string(2 * k), 4 * kNumFeat, kNumFeat, 9, st)) return 1;
+      } else {
+        h->upsample.resize(1);
+        if (make_gemm_w(h, &h->upsample[0], "upsample.0", 9 * kNumFeat, kNumFeat, 9, st)) return 1;
+      }
+      if (make_gemm_w(h, &h->conv_last, "conv_last", ic, kNumFeat, 9, st)) return 1;
+      break;
+    }
+    case HITSIR_UP_PIXELSHUFFLEDIRECT:
+      h->upsample.resize(1);
+      if (make_gemm_w(h, &h->upsample[0], "upsample.0", s * s * ic, C, 9, st)) return 1;
+      break;
+    case HITSIR_UP_NEAREST_CONV:
+      if (make_gemm_w(h, &h->conv_before_upsample, "conv_before_upsample.0", kNumFeat, C, 9, st)) return 1;
+      if (make_gemm_w(h, &h->conv_up1, "conv_up1", kNumFeat, kNumFeat, 9, st)) return 1;
+      if (make_gemm_w(h, &h->conv_up2, "conv_up2", kNumFeat, kNumFeat, 9, st)) return 1;
+      if (make_gemm_w(h, &h->conv_hr, "conv_hr", kNumFeat, kNumFeat, 9, st)) return 1;
+      if (make_gemm_w(h, &h->conv_last, "conv_last", ic, kNumFeat, 9, st)) return 1;
+      break;
+    default:
+      if (make_gemm_w(h, &h->conv_last, "conv_last", ic, C, 9, st)) return 1;
+      break;
+  }
+  h->finalized = true;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------
+struct Workspace {
+  size_t bytes = 0;
+  float *P = nullptr, *Q = nullptr, *S = nullptr;        // fp32 [N,180]: layer stream, working stream, shallow features
+  bf16 *xb0 = nullptr, *xb1 = nullptr;                   // bf16 [N,192] shadows (contiguous: also A0 [N,<=384])
+  bf16* T = nullptr;                                     // bf16 [NpMax,192] qkv tokens on the padded map
+  float *cavg = nullptr, *cmax = nullptr;                // [NpMax]
+  float *part_sum = nullptr, *part_max = nullptr, *s1 = nullptr, *s2 = nullptr;
+  float *scc_part = nullptr, *scc_fin = nullptr;
+  bf16* outsc = nullptr;                                 // bf16 [N,192]
+  bf16 *H1 = nullptr, *H2 = nullptr;                     // bf16 [N,384] (contiguous: also G [N,768], A1|A2 fp32)
+  float *havg, *hmax, *wavg, *wmax, *c_att, *h_att, *w_att;
+  bf16* up = nullptr;                                    // upsampler scratch
+  size_t up_bytes = 0;
+  int nparts = 1;
+};
+
+struct Bump {
+  uint8_t* base; size_t off = 0;
+  template <class T> T* take(size_t count) {
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+int scc_parts(int L) {
+  if (L <= 256) return 1;
+  for (int p = 2; p <= L; ++p)
+    if (L % p == 0 && L / p <= 256) return p;
+  return L;
+}
+
+int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Workspace* ws) {
+  const HitsirConfig& c = h->cfg;
+  const size_t N = (size_t)B * H * W;
+  size_t np_max = N;
+  long long part_max_f = 0, fin_max_f = 0;
+  int max_depth = 0;
+  for (int i = 0; i < c.num_layers; ++i) max_depth = c.depths[i] > max_depth ? c.depths[i] : max_depth;
+  for (int j = 0; j < max_depth; ++j) {
+    const int w = win_of(c, j);
+    const int Hp = round_up(H, w), Wp = round_up(W, w);
+    if (Hp - H >= H || Wp - W >= W) {
+      set_error("Padding size should be less than the corresponding input dimension, but got: padding (%d, %d) for input %dx%d (window %d)",
+                Wp - W, Hp - H, H, W, w);
+      return HITSIR_ERR_INPUT_TOO_SMALL;
+    }
+    const size_t np = (size_t)B * Hp * Wp;
+    np_max = np > np_max ? np : np_max;
+    SccGeom g;
+    g.pg = PadGeom{B, H, W, Hp, Wp};
+    g.w = w; g.base = w < c.base_win_size[0] ? w : c.base_win_size[0]; g.r = w / g.base;
+    g.L = w * w; g.Lb = g.base * g.base; g.nWy = Hp / w; g.nWx = Wp / w; g.parts = scc_parts(g.L);
+    long long pf, ff;
+    scc_workspace_floats(g, &pf, &ff);
+    part_max_f = pf > part_max_f ? pf : part_max_f;
+    fin_max_f = ff > fin_max_f ? ff : fin_max_f;
+  }
+  Bump b{reinterpret_cast<uint8_t*>(base)};
+  ws->P = b.take<float>(N * kC);
+  ws->Q = b.take<float>(N * kC);
+  ws->S = b.take<float>(N * kC);
+  ws->xb0 = b.take<bf16>(N * kCp * 2);   // xb0 | xb1 contiguous
+  ws->xb1 = ws->xb0 ? ws->xb0 + N * kCp : nullptr;
+  ws->T = b.take<bf16>(np_max * kCp);
+  ws->cavg = b.take<float>(np_max);
+  ws->cmax = b.take<float>(np_max);
+  ws->nparts = 64;
+  ws->part_sum = b.take<float>((size_t)B * ws->nparts * kC);
+  ws->part_max = b.take<float>((size_t)B * ws->nparts * kC);
+  ws->s1 = b.take<float>((size_t)B * kC);
+  ws->s2 = b.take<float>((size_t)B * kC);
+  ws->scc_part = b.take<float>((size_t)part_max_f);
+  ws->scc_fin = b.take<float>((size_t)fin_max_f);
+  ws->outsc = b.take<bf16>(N * kCp);
+  ws->H1 = b.take<bf16>(N * kHidp * 2);  // H1 | H2 contiguous
+  ws->H2 = ws->H1 ? ws->H1 + N * kHidp : nullptr;
+  ws->havg = b.take<float>((size_t)B * kC * W);
+  ws->hmax = b.take<float>((size_t)B * kC * W);
+  ws->wavg = b.take<float>((size_t)B * kC * H);
+  ws->wmax = b.take<float>((size_t)B * kC * H);
+  ws->c_att = b.take<float>(N);
+  ws->h_att = b.take<float>((size_t)B * kC * W);
+  ws->w_att = b.take<float>((size_t)B * kC * H);
+  // upsampler scratch (bf16 elements)
+  size_t up = 0;
+  const int s = c.upscale;
+  switch (c.upsampler) {
+    case HITSIR_UP_NEAREST_CONV: up = N * kNumFeat * (size_t)(1 + 4 + 4 + 16 + 16); break;   // U0, U0up, U1, U1up(/U3), U2
+    case HITSIR_UP_PIXELSHUFFLE: up = N * kNumFeat * (size_t)(1 + 4 + (s > 2 ? s * s : 0)); break;
+    default: up = 0; break;
+  }
+  ws->up_bytes = up * sizeof(bf16);
+  ws->up = b.take<bf16>(up);
+  ws->bytes = (b.off + 255) & ~(size_t)255;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+struct Fwd {
+  HitsirHandle* h;
+  cudaStream_t st;
+  int B, H, W;
+  long long N;
+  Workspace ws;
+  bool stopped = false;
+};
+
+// returns 1 on error, sets f.stopped when the requested tap asked to stop
+int do_tap(Fwd& f, const char* name, const void* src, int is_bf16, int ld, long long rows, int cols) {
+  Tap& t = f.h->tap;
+  if (t.dst == nullptr || t.name != name) return 0;
+  if (rows * cols > t.floats) { set_error("tap '%s' needs %lld floats, destination has %lld", name, rows * cols, (long long)t.floats); return HITSIR_ERR_INVALID; }
+  if (launch_f32_to_f32_tap(src, is_bf16, ld, t.dst, rows, cols, f.st)) return 1;
+  f.h->launches++;
+  if (t.stop) f.stopped = true;
+  return 0;
+}
+
+void base_params(GemmParams& p, const GemmW& w) {
+  memset(&p, 0, sizeof(p));
+  p.n_tiles = w.Npad / w.BN;
+  p.num_kb = w.K / 64;
+  p.cblocks = p.num_kb;
+  p.bias = w.b;
+  p.Wp = w.w; p.ldw = w.K;
+  p.ps = 1;
+  p.slope = 1.f;
+}
+
+int run_gemm(Fwd& f, const GemmW& w, GemmParams& p, const CUtensorMap& ta) {
+  f.h->launches++;
+  if (f.h->simt) return launch_simt_gemm(w.BN, p, f.st);
+  return launch_umma_gemm(w.BN, p, ta, w.tm, f.h->num_sms, f.st);
+}
+
+// token-major linear: A [M, lda] bf16 (lda == w.K)
+int linear(Fwd& f, const GemmW& w, const bf16* A, long long M, GemmParams& p) {
+  p.conv = 0; p.M = (int)M; p.m_tiles = (int)cdiv64(M, 128);
+  p.A = A; p.lda = w.K;
+  CUtensorMap ta;
+  if (!f.h->simt && make_tmap_2d(&ta, A, (uint64_t)w.K, (uint64_t)M, (uint64_t)w.K * 2, 64, 128)) return 1;
+  return run_gemm(f, w, p, ta);
+}
+
+// 3x3 conv over NHWC bf16 [B,H,W,Cpad]
+int conv3(Fwd& f, const GemmW& w, const bf16* A, int B, int H, int W, int Cpad, GemmParams& p) {
+  p.conv = 1; p.B = B; p.H = H; p.W = W;
+  p.tiles_x = cdiv(W, 16); p.tiles_y = cdiv(H, 8);
+  p.m_tiles = B * p.tiles_x * p.tiles_y;
+  p.cblocks = Cpad / 64;
+  p.A = A; p.lda = Cpad;
+  if (w.K != 9 * Cpad) { set_error("conv3: packed K %d != 9*%d", w.K, Cpad); return 1; }
+  CUtensorMap ta;
+  if (!f.h->simt && make_tmap_nhwc(&ta, A, B, H, W, Cpad, 64, 16, 8)) return 1;
+  return run_gemm(f, w, p, ta);
+}
+
+#define RUN(expr) do { int _r = (expr); if (_r) return _r; } while (0)
+#define TAP(name, src, is_bf16, ld, rows, cols) do { RUN(do_tap(f, name, src, is_bf16, ld, rows, cols)); if (f.stopped) return 0; } while (0)
+
+int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
+  // HierarchicalTransformerBlock.forward (:676-706); xin -> xout after the attention half, then in place on xout
+  HitsirHandle* h = f.h;
+  const HitsirConfig& c = h->cfg;
+  Workspace& ws = f.ws;
+  const BlockW& bw = h->blocks[i][j];
+  const std::string tn = "block" + std::to_string(i) + "." + std::to_string(j);
+  const int w = bw.win;
+  SccGeom g;
+  g.pg = PadGeom{f.B, f.H, f.W, round_up(f.H, w), round_up(f.W, w)};
+  g.w = w; g.base = bw.base; g.r = bw.r; g.L = w * w; g.Lb = bw.base * bw.base;
+  g.nWy = g.pg.Hp / w; g.nWx = g.pg.Wp / w; g.parts = scc_parts(g.L);
+  const long long Np = (long long)f.B * g.pg.Hp * g.pg.Wp;
+  if (c.is_channel_spatial_attn) {
+    RUN(launch_sca_stats(xin, g.pg, ws.cavg, ws.cmax, ws.part_sum, ws.part_max, ws.nparts, f.st)); h->launches++;
+    RUN(launch_sca_mlp(ws.part_sum, ws.part_max, ws.nparts, g.pg, bw.casa, ws.s1, ws.s2, f.st)); h->launches++;
+  }
+  RUN(launch_qkv_build(xin, g.pg, c.is_channel_spatial_attn, ws.cavg, ws.cmax, ws.s1, ws.s2, bw.casa, ws.T, f.st)); h->launches++;
+  TAP((tn + ".qkv").c_str(), ws.T, 1, kCp, Np, kC);
+  RUN(launch_scc(ws.T, g, bw.scc, ws.scc_part, ws.scc_fin, ws.outsc, f.st)); h->launches += (g.parts > 1 ? 3 : 1);
+  TAP((tn + ".scc").c_str(), ws.outsc, 1, kCp, f.N, kC);
+  GemmParams p;
+  // proj + norm1 + residual (:597, :700-703)
+  base_params(p, bw.proj);
+  p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g1; p.beta = bw.b1; p.res = xin; p.ldr = kC;
+  p.out_f32 = xout; p.ldf = kC; p.out_bf16 = ws.xb0; p.ldb = kCp;
+  RUN(linear(f, bw.proj, ws.outsc, f.N, p));
+  TAP((tn + ".attn").c_str(), xout, 0, kC, f.N, kC);
+  // ConvFFN (:39-46): fc1 + GELU
+  base_params(p, bw.fc1);
+  p.epi = EPI_STORE; p.act = ACT_GELU; p.n_real = kHid; p.out_bf16 = ws.H1; p.ldb = kHidp;
+  RUN(linear(f, bw.fc1, ws.xb0, f.N, p));
+  RUN(launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, f.st)); h->launches++;
+  // fc2 + norm2 + residual (:704)
+  base_params(p, bw.fc2);
+  p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g2; p.beta = bw.b2; p.res = xout; p.ldr = kC;
+  p.out_f32 = xout; p.ldf = kC; p.out_bf16 = ws.xb0; p.ldb = kCp;
+  RUN(linear(f, bw.fc2, ws.H2, f.N, p));
+  TAP(tn.c_str(), xout, 0, kC, f.N, kC);
+  return 0;
+}
+
+int union_attention(Fwd& f, int u, const float* a, const float* b, float* out) {
+  // UnionAttention.forward (:113-133) on X = a (+ b)
+  HitsirHandle* h = f.h;
+  Workspace& ws = f.ws;
+  RUN(launch_ua_stats(a, b, f.B, f.H, f.W, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, f.st)); h->launches += 2;
+  RUN(launch_ua_small_convs(f.B, f.H, f.W, h->ua[u].small, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, ws.c_att, ws.h_att, ws.w_att, f.st));
+  h->launches++;
+  RUN(launch_ua_build(f.B, f.H, f.W, ws.c_att, ws.h_att, ws.w_att, ws.outsc, f.st)); h->launches++;
+  GemmParams p;
+  base_params(p, h->ua[u].conv_last);
+  p.epi = EPI_STORE; p.n_real = kC; p.out_f32 = out; p.ldf = kC;
+  return conv3(f, h->ua[u].conv_last, ws.outsc, f.B, f.H, f.W, kCp, p);
+}
+
+int forward_impl(Fwd& f, const float* x, float* y) {
+  HitsirHandle* h = f.h;
+  const HitsirConfig& c = h->cfg;
+  Workspace& ws = f.ws;
+  const int B = f.B, H = f.H, W = f.W;
+  const long long N = f.N;
+  GemmParams p;
+  // ---- mean shift + shallow features (:1310-1311, :1315/1322/1328/1337) + patch_embed LayerNorm (:975-983)
+  bf16* A0 = ws.xb0;   // [N, first_kp <= 384] aliases xb0|xb1, dead before the second GEMM writes xb0
+  RUN(launch_entry_im2col(x, A0, B, H, W, c.in_chans, h->first_f, h->first_kp, h->mean, c.img_range, f.st)); h->launches++;
+  const float* pe_g = P(h, "patch_embed.norm.weight");
+  const float* pe_b = P(h, "patch_embed.norm.bias");
+  if (c.is_mult_size_conv_feat_extract) {
+    bf16* G = ws.H1;   // [N,768] aliases H1|H2
+    base_params(p, h->first);
+    p.epi = EPI_MSGATE; p.n_real = kC; p.out_bf16 = G; p.ldb = 4 * kCp;
+    RUN(linear(f, h->first, A0, N, p));
+    base_params(p, h->first_last);
+    p.epi = EPI_LN; p.n_real = kC; p.gamma = pe_g; p.beta = pe_b;
+    p.out2_f32 = ws.S; p.ldf2 = kC; p.out_f32 = ws.P; p.ldf = kC;
+    RUN(linear(f, h->first_last, G, N, p));
+  } else {
+    // the plain conv_first reads A0 (in xb0|xb1) so it must not write a bf16 shadow there
+    base_params(p, h->first);
+    p.epi = EPI_LN; p.n_real = kC; p.gamma = pe_g; p.beta = pe_b;
+    p.out2_f32 = ws.S; p.ldf2 = kC; p.out_f32 = ws.P; p.ldf = kC;
+    RUN(linear(f, h->first, A0, N, p));
+  }
+  TAP("shallow", ws.S, 0, kC, N, kC);
+  TAP("embed", ws.P, 0, kC, N, kC);
+  // ---- deep features: RHTB stack (:1296-1297, :928-936)
+  for (int i = 0; i < c.num_layers; ++i) {
+    for (int j = 0; j < c.depths[i]; ++j) {
+      RUN(forward_block(f, i, j, j == 0 ? ws.P : ws.Q, ws.Q));
+      if (f.stopped) return 0;
+    }
+    base_params(p, h->layer_conv[i]);
+    p.epi = EPI_STORE; p.n_real = kC; p.res = ws.P; p.ldr = kC; p.out_f32 = ws.P; p.ldf = kC;
+    RUN(conv3(f, h->layer_conv[i], ws.xb0, B, H, W, kCp, p));
+    TAP(("layer" + std::to_string(i)).c_str(), ws.P, 0, kC, N, kC);
+  }
+  // ---- final norm + conv_after_body (:1299-1300, :1317/1324/1330/1339)
+  RUN(launch_ln_rows(ws.P, P(h, "norm.weight"), P(h, "norm.bias"), ws.xb0, nullptr, N, f.st)); h->launches++;
+  TAP("norm", ws.xb0, 1, kCp, N, kC);
+  float* CAB = ws.Q;
+  base_params(p, h->conv_after_body);
+  p.epi = EPI_STORE; p.n_real = kC; p.out_f32 = CAB; p.ldf = kC;
+  RUN(conv3(f, h->conv_after_body, ws.xb0, B, H, W, kCp, p));
+  TAP("conv_after_body", CAB, 0, kC, N, kC);
+  // ---- fusion(conv_after_body(deep), shallow): positional binding (:1330 -> :145)
+  bf16* F = ws.xb1;
+  if (c.is_fusion) {
+    float* A1 = reinterpret_cast<float*>(ws.H1);       // [N,180] fp32 x2 inside H1|H2 (N*1536 B >= 2*N*720 B)
+    float* A2 = A1 + N * kC;
+    float* A3 = ws.P;                                  // the stream buffer is dead after the final norm
+    RUN(union_attention(f, 0, CAB, nullptr, A1));
+    RUN(union_attention(f, 1, CAB, ws.S, A2));
+    RUN(union_attention(f, 2, ws.S, nullptr, A3));
+    float* tapdst = (h->tap.dst != nullptr && h->tap.name == "fused") ? h->tap.dst : nullptr;
+    if (tapdst != nullptr && N * kC > h->tap.floats) { set_error("tap 'fused' destination too small"); return HITSIR_ERR_INVALID; }
+    RUN(launch_fusion_combine(CAB, ws.S, A1, A2, A3, F, tapdst, N, f.st)); h->launches++;
+    if (tapdst != nullptr && h->tap.stop) { f.stopped = true; return 0; }
+  } else {
+    RUN(launch_add_to_bf16(CAB, ws.S, F, N, f.st)); h->launches++;
+    TAP("fused", F, 1, kCp, N, kC);
+  }
+  // ---- reconstruction (:1313-1340)
+  const int s = c.upscale;
+  auto last_params = [&](GemmParams& q, const GemmW& w, int ps) {
+    base_params(q, w);
+    q.epi = EPI_SHUFFLE_NCHW; q.ps = ps; q.n_real = c.in_chans * ps * ps; q.shuf_c = c.in_chans;
+    q.out_scale = 1.0f / c.img_range;
+    for (int k = 0; k < 4; ++k) q.mean[k] = h->mean[k];
+    q.out_f32 = y;
+  };
+  if (c.upsampler == HITSIR_UP_NEAREST_CONV) {
+    bf16* U0 = ws.up;
+    bf16* U0up = U0 + N * kNumFeat;
+    bf16* U1 = U0up + 4 * N * kNumFeat;
+    bf16* U1up = U1 + 4 * N * kNumFeat;
+    bf16* U2 = U1up + 16 * N * kNumFeat;
+    bf16* U3 = U1up;
+    base_params(p, h->conv_before_upsample);
+    p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.01f; p.n_real = kNumFeat; p.out_bf16 = U0; p.ldb = kNumFeat;   // nn.LeakyReLU() default slope (:1251)
+    RUN(conv3(f, h->conv_before_upsample, F, B, H, W, kCp, p));
+    TAP("conv_before_upsample", U0, 1, kNumFeat, N, kNumFeat);
+    RUN(launch_upsample_nearest2(U0, U0up, B, H, W, kNumFeat, f.st)); h->launches++;
+    base_params(p, h->conv_up1);
+    p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = kNumFeat; p.out_bf16 = U1; p.ldb = kNumFeat;
+    RUN(conv3(f, h->conv_up1, U0up, B, 2 * H, 2 * W, kNumFeat, p));
+    TAP("up1", U1, 1, kNumFeat, 4 * N, kNumFeat);
+    RUN(launch_upsample_nearest2(U1, U1up, B, 2 * H, 2 * W, kNumFeat, f.st)); h->launches++;
+    base_params(p, h->conv_up2);
+    p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = kNumFeat; p.out_bf16 = U2; p.ldb = kNumFeat;
+    RUN(conv3(f, h->conv_up2, U1up, B, 4 * H, 4 * W, kNumFeat, p));
+    TAP("up2", U2, 1, kNumFeat, 16 * N, kNumFeat);
+    base_params(p, h->conv_hr);
+    p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = kNumFeat; p.out_bf16 = U3; p.ldb = kNumFeat;
+    RUN(conv3(f, h->conv_hr, U2, B, 4 * H, 4 * W, kNumFeat, p));
+    TAP("hr", U3, 1, kNumFeat, 16 * N, kNumFeat);
+    last_params(p, h->conv_last, 1);
+    RUN(conv3(f, h->conv_last, U3, B, 4 * H, 4 * W, kNumFeat, p));
+  } else if (c.upsampler == HITSIR_UP_PIXELSHUFFLE) {
+    bf16* U0 = ws.up;
+    bf16* Ua = U0 + N * kNumFeat;
+    bf16* Ub = Ua + 4 * N * kNumFeat;
+    base_params(p, h->conv_before_upsample);
+    p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.01f; p.n_real = kNumFeat; p.out_bf16 = U0; p.ldb = kNumFeat;
+    RUN(conv3(f, h->conv_before_upsample, F, B, H, W, kCp, p));
+    TAP("conv_before_upsample", U0, 1, kNumFeat, N, kNumFeat);
+    const bf16* cur = U0;
+    int ch = H, cw = W;
+    if ((s & (s - 1)) == 0) {
+      for (size_t k = 0; k < h->upsample.size(); ++k) {
+        bf16* dst = (k % 2 == 0) ? Ua : Ub;
+        if (k >= 2) { set_error("pixelshuffle upscale > 4 not supported by this build"); return HITSIR_ERR_UNSUPPORTED; }
+        base_params(p, h->upsample[k]);
+        p.epi = EPI_SHUFFLE_BF16; p.ps = 2; p.n_real = 4 * kNumFeat; p.shuf_c = kNumFeat; p.out_bf16 = dst; p.ldb = kNumFeat;
+        RUN(conv3(f, h->upsample[k], cur, B, ch, cw, kNumFeat, p));
+        cur = dst; ch *= 2; cw *= 2;
+      }
+    } else {
+      base_params(p, h->upsample[0]);
+      p.epi = EPI_SHUFFLE_BF16; p.ps = 3; p.n_real = 9 * kNumFeat; p.shuf_c = kNumFeat; p.out_bf16 = Ub; p.ldb = kNumFeat;
+      RUN(conv3(f, h->upsample[0], cur, B, ch, cw, kNumFeat, p));
+      cur = Ub; ch *= 3; cw *= 3;
+    }
+    last_params(p, h->conv_last, 1);
+    RUN(conv3(f, h->conv_last, cur, B, ch, cw, kNumFeat, p));
+  } else if (c.upsampler == HITSIR_UP_PIXELSHUFFLEDIRECT) {
+    last_params(p, h->upsample[0], s);
+    RUN(conv3(f, h->upsample[0], F, B, H, W, kCp, p));
+  } else {
+    set_error("upsampler=None (x + conv_last(res)) is not implemented in this build");
+    return HITSIR_ERR_UNSUPPORTED;
+  }
+  return 0;
+}
+
+}  // namespace
+
+// ==========================================================================================
+// C ABI
+// ==========================================================================================
+extern "C" {
+
+HITSIR_API const char* hitsir_last_error(void) { return g_err; }
+HITSIR_API const char* hitsir_version(void) { return "hitsir_b200 0.1 (sm_100a, tcgen05+TMA)"; }
+
+HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
+  if (!cfg || !out) { set_error("hitsir_create: null argument"); return HITSIR_ERR_INVALID; }
+  *out = nullptr;
+  int rc = validate_config(*cfg);
+  if (rc) return rc;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) { set_error("hitsir_create: no CUDA device (%s); this library has no CPU path", cudaGetErrorString(e)); return HITSIR_ERR_CUDA; }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) { set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e)); return HITSIR_ERR_CUDA; }
+  if (prop.major != 10) { set_error("hitsir_b200 needs an sm_100 (Blackwell B200) device, found sm_%d%d (%s)", prop.major, prop.minor, prop.name); return HITSIR_ERR_CUDA; }
+  HitsirHandle* h = new HitsirHandle();
+  h->cfg = *cfg;
+  h->device = dev;
+  h->num_sms = prop.multiProcessorCount;
+  if (cfg->in_chans == 3) { h->mean[0] = 0.485f; h->mean[1] = 0.456f; h->mean[2] = 0.4060f; }   // (:1128)
+  const char* env = getenv("HITSIR_GEMM");
+  h->simt = env && strcmp(env, "simt") == 0;
+  build_param_list(h);
+  e = cudaMalloc(reinterpret_cast<void**>(&h->arena), h->arena_floats * sizeof(float));
+  if (e != cudaSuccess) { set_error("cudaMalloc(param arena): %s", cudaGetErrorString(e)); delete h; return HITSIR_ERR_CUDA; }
+  *out = h;
+  return 0;
+}
+
+HITSIR_API void hitsir_destroy(HitsirHandle* h) {
+  if (!h) return;
+  free_owned(h);
+  if (h->arena) cudaFree(h->arena);
+  delete h;
+}
+
+HITSIR_API int hitsir_num_params(const HitsirHandle* h) { return h ? (int)h->params.size() : 0; }
+HITSIR_API const char* hitsir_param_name(const HitsirHandle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->params.size()) return nullptr;
+  return h->params[i].name.c_str();
+}
+HITSIR_API int64_t hitsir_param_numel(const HitsirHandle* h, int i) {
+  if (!h || i < 0 || i >= (int)h->params.size()) return -1;
+  return h->params[i].numel;
+}
+
+HITSIR_API int hitsir_set_param(HitsirHandle* h, const char* name, const float* data, int64_t numel, void* stream) {
+  if (!h || !name || !data) { set_error("hitsir_set_param: null argument"); return HITSIR_ERR_INVALID; }
+  auto it = h->index.find(name);
+  if (it == h->index.end()) { set_error("Unexpected key(s) in state_dict: \"%s\"", name); return HITSIR_ERR_INVALID; }
+  ParamSpec& p = h->params[it->second];
+  if (p.numel != numel) { set_error("size mismatch for %s: expected %lld elements, got %lld", name, (long long)p.numel, (long long)numel); return HITSIR_ERR_INVALID; }
+  HITSIR_CHECK(cudaMemcpyAsync(h->arena + p.offset, data, (size_t)numel * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  p.set = true;
+  h->finalized = false;
+  return 0;
+}
+
+HITSIR_API int hitsir_finalize_weights(HitsirHandle* h, void* stream) {
+  if (!h) { set_error("null handle"); return HITSIR_ERR_INVALID; }
+  return finalize(h, (cudaStream_t)stream);
+}
+
+HITSIR_API int hitsir_workspace_bytes(const HitsirHandle* h, int B, int H, int W, size_t* bytes) {
+  if (!h || !bytes || B < 1 || H < 1 || W < 1) { set_error("hitsir_workspace_bytes: bad argument"); return HITSIR_ERR_INVALID; }
+  Workspace ws;
+  int rc = layout_workspace(h, B, H, W, nullptr, &ws);
+  if (rc) return rc;
+  *bytes = ws.bytes;
+  return 0;
+}
+
+HITSIR_API int hitsir_forward(HitsirHandle* h, const float* x, float* y, int B, int H, int W, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !x || !y || !workspace) { set_error("hitsir_forward: null argument"); return HITSIR_ERR_INVALID; }
+  if (!h->finalized) { set_error("hitsir_forward: weights not finalized (call hitsir_set_param for every key, then hitsir_finalize_weights)"); return HITSIR_ERR_WEIGHTS; }
+  if ((long long)B * H * W * 16 >= 2147483647LL / 4) {
+    // row indices are kept in 32 bit inside the GEMM tile maps; 16x upsampled pixel counts must fit too
+    if ((long long)B * H * W * 16 >= 2147483647LL) { set_error("input too large: B*H*W*16 must be < 2^31"); return HITSIR_ERR_UNSUPPORTED; }
+  }
+  Fwd f;
+  f.h = h; f.st = (cudaStream_t)stream; f.B = B; f.H = H; f.W = W; f.N = (long long)B * H * W;
+  int rc = layout_workspace(h, B, H, W, workspace, &f.ws);
+  if (rc) return rc;
+  if (((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned"); return HITSIR_ERR_WORKSPACE; }
+  if (f.ws.bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", f.ws.bytes, workspace_bytes); return HITSIR_ERR_WORKSPACE; }
+  h->launches = 0;
+  rc = forward_impl(f, x, y);
+  return rc;
+}
+
+HITSIR_API int hitsir_forward_host(HitsirHandle* h, const float* host_x, float* host_y, int B, int H, int W, float* dev_x, float* dev_y,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !host_x || !host_y || !dev_x || !dev_y) { set_error("hitsir_forward_host: null argument"); return HITSIR_ERR_INVALID; }
+  const size_t in_b = (size_t)B * h->cfg.in_chans * H * W * sizeof(float);
+  const size_t out_b = in_b * h->cfg.upscale * h->cfg.upscale;
+  HITSIR_CHECK(cudaMemcpyAsync(dev_x, host_x, in_b, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  int rc = hitsir_forward(h, dev_x, dev_y, B, H, W, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  HITSIR_CHECK(cudaMemcpyAsync(host_y, dev_y, out_b, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  return 0;
+}
+
+HITSIR_API int hitsir_set_tap(HitsirHandle* h, const char* name, float* dst, int64_t dst_floats, int stop) {
+  if (!h) { set_error("null handle"); return HITSIR_ERR_INVALID; }
+  if (!name) { h->tap = Tap(); return 0; }
+  h->tap.name = name; h->tap.dst = dst; h->tap.floats = dst_floats; h->tap.stop = stop;
+  return 0;
+}
+
+HITSIR_API int64_t hitsir_last_launch_count(const HitsirHandle* h) { return h ? h->launches : 0; }
+
+HITSIR_API int hitsir_set_gemm_backend(HitsirHandle* h, const char* backend) {
+  if (!h || !backend) { set_error("null argument"); return HITSIR_ERR_INVALID; }
+  if (strcmp(backend, "umma") == 0) h->simt = false;
+  else if (strcmp(backend, "simt") == 0) h->simt = true;
+  else { set_error("unknown gemm backend '%s' (umma|simt)", backend); return HITSIR_ERR_INVALID; }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,472 @@
+// Bandwidth-bound glue kernels of the HiT-SIR-pro forward (everything that is not a dense
+// contraction or the window self-correlation): entry im2col, LayerNorm, depthwise 5x5 + GELU,
+// casa (SpatialChannelAttention) statistics and gating, UnionAttention/Fusion statistics and
+// gating, nearest upsampling.  Token-major (NHWC) throughout; 128-bit accesses where rows allow.
+#include "kernels.cuh"
+
+namespace hitsir {
+
+namespace {
+
+__device__ __forceinline__ int reflect_src(int i, int n) { return i < n ? i : 2 * (n - 1) - i; }   // F.pad 'reflect' (:672)
+
+// ---------------------------------------------------------------------------------------------
+__global__ void entry_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ a0, int B, int H, int W, int in_ch, int f, int Kp,
+                                    float m0, float m1, float m2, float img_range) {
+  const int chunks = Kp / 8;
+  const long long total = (long long)B * H * W * chunks;
+  const int half = f / 2, kreal = f * f * in_ch;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % chunks);
+    const long long pix = idx / chunks;
+    const int xw = (int)(pix % W); const long long t = pix / W; const int y = (int)(t % H); const int b = (int)(t / H);
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = ch * 8 + e;
+      float val = 0.f;
+      if (k < kreal) {
+        const int tap = k / in_ch, c = k - tap * in_ch;
+        const int yy = y + tap / f - half, xx = xw + tap % f - half;
+        if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+          const float mean = (in_ch == 3) ? (c == 0 ? m0 : (c == 1 ? m1 : m2)) : 0.f;
+          val = (__ldg(x + (((long long)b * in_ch + c) * H + yy) * W + xx) - mean) * img_range;
+        }
+      }
+      v[e] = val;
+    }
+    uint4 o = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+    *reinterpret_cast<uint4*>(a0 + pix * Kp + ch * 8) = o;
+  }
+}
+
+// one warp per row
+__global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                               bf16* __restrict__ ob, float* __restrict__ of, long long N) {
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+  for (long long row = warp0; row < N; row += nwarps) {
+    const float* r = x + row * kC;
+    float v[6];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const int c = lane + 32 * i; v[i] = c < kC ? r[c] : 0.f; s += v[i]; }
+    const float mean = warp_sum(s) / (float)kC;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) { const int c = lane + 32 * i; const float d = c < kC ? v[i] - mean : 0.f; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)kC + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = lane + 32 * i;
+      const float y = c < kC ? (v[i] - mean) * rstd * gamma[c] + beta[c] : 0.f;
+      if (ob != nullptr) ob[row * kCp + c] = __float2bfloat16(y);
+      if (of != nullptr && c < kC) of[row * kC + c] = y;
+    }
+  }
+}
+
+// thread = (pixel, 8 channels); h2 = h1 + gelu(dw5x5(h1) + b)
+__global__ void dwconv5_kernel(const bf16* __restrict__ h1, const float* __restrict__ wt, const float* __restrict__ bias, bf16* __restrict__ h2,
+                               int B, int H, int W) {
+  constexpr int groups = kHidp / 8;   // 48
+  const long long total = (long long)B * H * W * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int gidx = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int xw = (int)(pix % W); const long long t = pix / W; const int y = (int)(t % H); const int b = (int)(t / H);
+    const int c0 = gidx * 8;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = __ldg(bias + c0 + e);
+    float center[8];
+#pragma unroll
+    for (int ky = 0; ky < 5; ++ky) {
+      const int yy = y + ky - 2;
+      if (yy < 0 || yy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 5; ++kx) {
+        const int xx = xw + kx - 2;
+        if (xx < 0 || xx >= W) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(h1 + (((long long)b * H + yy) * W + xx) * kHidp + c0));
+        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (ky * 5 + kx) * kHidp + c0));
+        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (ky * 5 + kx) * kHidp + c0 + 4));
+        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+        acc[0] += f0.x * w0.x; acc[1] += f0.y * w0.y; acc[2] += f1.x * w0.z; acc[3] += f1.y * w0.w;
+        acc[4] += f2.x * w1.x; acc[5] += f2.y * w1.y; acc[6] += f3.x * w1.z; acc[7] += f3.y * w1.w;
+        if (ky == 2 && kx == 2) {
+          center[0] = f0.x; center[1] = f0.y; center[2] = f1.x; center[3] = f1.y;
+          center[4] = f2.x; center[5] = f2.y; center[6] = f3.x; center[7] = f3.y;
+        }
+      }
+    }
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = (c0 + e < kHid) ? center[e] + gelu_erf(acc[e]) : 0.f;
+    *reinterpret_cast<uint4*>(h2 + pix * kHidp + c0) =
+        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
+// thread = (output pixel, 16-byte chunk)
+__global__ void upsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
+  const int chunks = C / 8;
+  const int OH = 2 * H, OW = 2 * W;
+  const long long total = (long long)B * OH * OW * chunks;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(idx % chunks);
+    const long long pix = idx / chunks;
+    const int ox = (int)(pix % OW); const long long t = pix / OW; const int oy = (int)(t % OH); const int b = (int)(t / OH);
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * C + ch * 8));
+    *reinterpret_cast<uint4*>(out + pix * C + ch * 8) = u;
+  }
+}
+
+__global__ void fill_kernel(float* p, float v, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void tap_kernel(const void* src, int is_bf16, int ld, float* dst, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols; const int c = (int)(i - r * cols);
+    dst[i] = is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(src)[r * ld + c]) : reinterpret_cast<const float*>(src)[r * ld + c];
+  }
+}
+
+__global__ void add_to_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, bf16* __restrict__ out, long long N) {
+  const long long total = N * kCp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / kCp; const int c = (int)(i - r * kCp);
+    out[i] = __float2bfloat16(c < kC ? a[r * kC + c] + b[r * kC + c] : 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// casa statistics.  grid = (nparts, B); each CTA walks a slice of the padded map of one image,
+// one warp per padded pixel, and emits a deterministic partial (sum, max) per channel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sca_stats_kernel(const float* __restrict__ x, PadGeom g, float* __restrict__ cavg, float* __restrict__ cmax,
+                                                        float* __restrict__ part_sum, float* __restrict__ part_max, int nparts) {
+  __shared__ float s_sum[8][kCp];
+  __shared__ float s_max[8][kCp];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, part = blockIdx.x;
+  const int npix = g.Hp * g.Wp;
+  const int per = (npix + nparts - 1) / nparts;
+  const int p0 = part * per, p1 = min(npix, p0 + per);
+  float asum[6], amax[6];
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { asum[i] = 0.f; amax[i] = -INFINITY; }
+  for (int pp = p0 + warp; pp < p1; pp += 8) {
+    const int yp = pp / g.Wp, xp = pp - yp * g.Wp;
+    const float* r = x + (((long long)b * g.H + reflect_src(yp, g.H)) * g.W + reflect_src(xp, g.W)) * kC;
+    float s = 0.f, m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = lane + 32 * i;
+      if (c < kC) { const float v = r[c]; s += v; m = fmaxf(m, v); asum[i] += v; amax[i] = fmaxf(amax[i], v); }
+    }
+    s = warp_sum(s); m = warp_max(m);
+    if (lane == 0) { cavg[(long long)b * npix + pp] = s / (float)kC; cmax[(long long)b * npix + pp] = m; }
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { s_sum[warp][lane + 32 * i] = asum[i]; s_max[warp][lane + 32 * i] = amax[i]; }
+  __syncthreads();
+  if (threadIdx.x < kC) {
+    float s = 0.f, m = -INFINITY;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) { s += s_sum[wv][threadIdx.x]; m = fmaxf(m, s_max[wv][threadIdx.x]); }
+    part_sum[((long long)b * nparts + part) * kC + threadIdx.x] = s;
+    part_max[((long long)b * nparts + part) * kC + threadIdx.x] = m;
+  }
+}
+
+// one CTA per image: finish the global pools, then Linear C->18->C twice (no activation, :350-355)
+__global__ void __launch_bounds__(192) sca_mlp_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_max, int nparts, PadGeom g,
+                                                      CasaW w, float* __restrict__ s1, float* __restrict__ s2) {
+  __shared__ float avg[kC], mx[kC], h1[18], h2[18];
+  const int b = blockIdx.x, c = threadIdx.x;
+  if (c < kC) {
+    float s = 0.f, m = -INFINITY;
+    for (int p = 0; p < nparts; ++p) { s += part_sum[((long long)b * nparts + p) * kC + c]; m = fmaxf(m, part_max[((long long)b * nparts + p) * kC + c]); }
+    avg[c] = s / (float)(g.Hp * g.Wp); mx[c] = m;
+  }
+  __syncthreads();
+  if (c < 18) {
+    float a = w.l1f_b[c], bb = w.l2f_b[c];
+    for (int k = 0; k < kC; ++k) { a += w.l1f_w[c * kC + k] * avg[k]; bb += w.l2f_w[c * kC + k] * mx[k]; }
+    h1[c] = a; h2[c] = bb;
+  }
+  __syncthreads();
+  if (c < kC) {
+    float a = w.l1s_b[c], bb = w.l2s_b[c];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) { a += w.l1s_w[c * 18 + k] * h1[k]; bb += w.l2s_w[c * 18 + k] * h2[k]; }
+    s1[(long long)b * kC + c] = a; s2[(long long)b * kC + c] = bb;
+  }
+}
+
+// thread = (padded pixel, 8 channels)
+__global__ void qkv_build_kernel(const float* __restrict__ x, PadGeom g, int casa, const float* __restrict__ cavg, const float* __restrict__ cmax,
+                                 const float* __restrict__ s1, const float* __restrict__ s2, CasaW w, bf16* __restrict__ t) {
+  constexpr int groups = kCp / 8;   // 24
+  const long long total = (long long)g.B * g.Hp * g.Wp * groups;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int gi = (int)(idx % groups);
+    const long long pix = idx / groups;
+    const int xp = (int)(pix % g.Wp); const long long tt = pix / g.Wp; const int yp = (int)(tt % g.Hp); const int b = (int)(tt / g.Hp);
+    const int c0 = gi * 8;
+    float o[8];
+    if (c0 >= kC) {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = 0.f;
+    } else {
+      const float* r = x + (((long long)b * g.H + reflect_src(yp, g.H)) * g.W + reflect_src(xp, g.W)) * kC + c0;
+      // rows are 720 B (16-byte aligned), c0 multiple of 8 -> two float4 loads; the tail group (c0=176) has only 4 channels
+      const float4 v0 = *reinterpret_cast<const float4*>(r);
+      float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + 4 < kC) v1 = *reinterpret_cast<const float4*>(r + 4);
+      o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w;
+      if (casa) {
+        float a1[8], a2[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const int c = min(c0 + e, kC - 1); a1[e] = w.b1[c]; a2[e] = w.b2[c]; }
+        const float* ca = cavg + (long long)b * g.Hp * g.Wp;
+        const float* cm = cmax + (long long)b * g.Hp * g.Wp;
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap) {
+          const int yy = yp + tap / 3 - 1, xx = xp + tap % 3 - 1;
+          if (yy < 0 || yy >= g.Hp || xx < 0 || xx >= g.Wp) continue;    // zero padding of the PADDED map
+          const float va = ca[yy * g.Wp + xx], vm = cm[yy * g.Wp + xx];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = min(c0 + e, kC - 1);
+            a1[e] += w.w1[tap * kC + c] * va;
+            a2[e] += w.w2[tap * kC + c] * vm;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = c0 + e;
+          if (c < kC) o[e] += 0.5f * (lrelu(a1[e], 0.2f) * s1[(long long)b * kC + c] + lrelu(a2[e], 0.2f) * s2[(long long)b * kC + c]);
+          else o[e] = 0.f;
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(t + pix * kCp + c0) =
+        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// UnionAttention statistics.  X = a (+ b).
+//   rows kernel : CTA per (b, y): channel mean/max per pixel + mean/max over W per channel.
+//   cols kernel : CTA per (b, x): mean/max over H per channel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192) ua_rows_kernel(const float* __restrict__ a, const float* __restrict__ bsrc, int B, int H, int W,
+                                                      float* __restrict__ cavg, float* __restrict__ cmax, float* __restrict__ wavg, float* __restrict__ wmax) {
+  __shared__ float red_s[6], red_m[6];
+  const int b = blockIdx.x / H, y = blockIdx.x - b * H;
+  const int c = threadIdx.x;
+  const int warp = c >> 5, lane = c & 31;
+  float rs = 0.f, rm = -INFINITY;
+  for (int xw = 0; xw < W; ++xw) {
+    const long long off = (((long long)b * H + y) * W + xw) * kC + c;
+    float v = 0.f;
+    if (c < kC) { v = a[off]; if (bsrc != nullptr) v += bsrc[off]; rs += v; rm = fmaxf(rm, v); }
+    const float ws = warp_sum(c < kC ? v : 0.f);
+    const float wm = warp_max(c < kC ? v : -INFINITY);
+    if (lane == 0) { red_s[warp] = ws; red_m[warp] = wm; }
+    __syncthreads();
+    if (c == 0) {
+      float s = 0.f, m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { s += red_s[i]; m = fmaxf(m, red_m[i]); }
+      cavg[((long long)b * H + y) * W + xw] = s / (float)kC;
+      cmax[((long long)b * H + y) * W + xw] = m;
+    }
+    __syncthreads();
+  }
+  if (c < kC) {
+    wavg[((long long)b * kC + c) * H + y] = rs / (float)W;
+    wmax[((long long)b * kC + c) * H + y] = rm;
+  }
+}
+
+__global__ void __launch_bounds__(192) ua_cols_kernel(const float* __restrict__ a, const float* __restrict__ bsrc, int B, int H, int W,
+                                                      float* __restrict__ havg, float* __restrict__ hmax) {
+  const int b = blockIdx.x / W, xw = blockIdx.x - b * W;
+  const int c = threadIdx.x;
+  if (c >= kC) return;
+  float s = 0.f, m = -INFINITY;
+  for (int y = 0; y < H; ++y) {
+    const long long off = (((long long)b * H + y) * W + xw) * kC + c;
+    float v = a[off]; if (bsrc != nullptr) v += bsrc[off];
+    s += v; m = fmaxf(m, v);
+  }
+  havg[((long long)b * kC + c) * W + xw] = s / (float)H;
+  hmax[((long long)b * kC + c) * W + xw] = m;
+}
+
+// 3x3 conv 2->1 on a (rows x cols) plane pair, zero padded.  plane layouts: avg/max [B][rows][cols]
+__device__ __forceinline__ float conv2to1(const float* __restrict__ pa, const float* __restrict__ pm, int rows, int cols, int rr, int cc,
+                                          const float* __restrict__ w, float bias) {
+  float acc = bias;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int r2 = rr + ky - 1;
+    if (r2 < 0 || r2 >= rows) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int c2 = cc + kx - 1;
+      if (c2 < 0 || c2 >= cols) continue;
+      acc += w[ky * 3 + kx] * pa[(long long)r2 * cols + c2] + w[9 + ky * 3 + kx] * pm[(long long)r2 * cols + c2];
+    }
+  }
+  return acc;
+}
+
+__global__ void ua_small_convs_kernel(int B, int H, int W, UaW w, const float* __restrict__ cavg, const float* __restrict__ cmax,
+                                      const float* __restrict__ havg, const float* __restrict__ hmax, const float* __restrict__ wavg,
+                                      const float* __restrict__ wmax, float* __restrict__ c_att, float* __restrict__ h_att, float* __restrict__ w_att) {
+  const long long n1 = (long long)B * H * W, n2 = (long long)B * kC * W, n3 = (long long)B * kC * H;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2 + n3; idx += (long long)gridDim.x * blockDim.x) {
+    if (idx < n1) {                 // conv1 over the (H, W) plane                       (:120-122)
+      const int b = (int)(idx / (H * W)); const int rem = (int)(idx - (long long)b * H * W);
+      c_att[idx] = conv2to1(cavg + (long long)b * H * W, cmax + (long long)b * H * W, H, W, rem / W, rem % W, w.c1_w, w.c1_b[0]);
+    } else if (idx < n1 + n2) {     // conv2 over the (channel, W) plane                 (:124-126)
+      const long long i = idx - n1;
+      const int b = (int)(i / (kC * W)); const int rem = (int)(i - (long long)b * kC * W);
+      h_att[i] = conv2to1(havg + (long long)b * kC * W, hmax + (long long)b * kC * W, kC, W, rem / W, rem % W, w.c2_w, w.c2_b[0]);
+    } else {                        // conv3 over the (channel, H) plane                 (:128-130)
+      const long long i = idx - n1 - n2;
+      const int b = (int)(i / (kC * H)); const int rem = (int)(i - (long long)b * kC * H);
+      w_att[i] = conv2to1(wavg + (long long)b * kC * H, wmax + (long long)b * kC * H, kC, H, rem / H, rem % H, w.c3_w, w.c3_b[0]);
+    }
+  }
+}
+
+__global__ void ua_build_kernel(int B, int H, int W, const float* __restrict__ c_att, const float* __restrict__ h_att, const float* __restrict__ w_att,
+                                bf16* __restrict__ s) {
+  const long long total = (long long)B * H * W * kCp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % kCp);
+    const long long pix = idx / kCp;
+    const int xw = (int)(pix % W); const long long t = pix / W; const int y = (int)(t % H); const int b = (int)(t / H);
+    float v = 0.f;
+    if (c < kC) v = c_att[pix] + w_att[((long long)b * kC + c) * H + y] + h_att[((long long)b * kC + c) * W + xw];   // (:133)
+    s[idx] = __float2bfloat16(v);
+  }
+}
+
+__global__ void fusion_combine_kernel(const float* __restrict__ first, const float* __restrict__ second, const float* __restrict__ a1,
+                                      const float* __restrict__ a2, const float* __restrict__ a3, bf16* __restrict__ out, float* __restrict__ of, long long N) {
+  const long long total = N * kCp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long r = idx / kCp; const int c = (int)(idx - r * kCp);
+    float v = 0.f;
+    if (c < kC) {
+      const long long i = r * kC + c;
+      const float att = sigmoidf_(a2[i]);                                       // (:152)
+      v = first[i] * sigmoidf_(a1[i] * att) + second[i] * sigmoidf_(a3[i] * (1.f - att));   // (:155-162)
+      if (of != nullptr) of[i] = v;
+    }
+    out[idx] = __float2bfloat16(v);
+  }
+}
+
+inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+int launch_entry_im2col(const float* x, bf16* a0, int B, int H, int W, int in_ch, int f, int Kp, const float* mean3, float img_range, cudaStream_t st) {
+  const long long total = (long long)B * H * W * (Kp / 8);
+  entry_im2col_kernel<<<grid_for(total, 256), 256, 0, st>>>(x, a0, B, H, W, in_ch, f, Kp, mean3[0], mean3[1], mean3[2], img_range);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* ob, float* of, long long N, cudaStream_t st) {
+  ln_rows_kernel<<<grid_for(N * 32, 256), 256, 0, st>>>(x, gamma, beta, ob, of, N);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, bf16* h2, int B, int H, int W, cudaStream_t st) {
+  const long long total = (long long)B * H * W * (kHidp / 8);
+  dwconv5_kernel<<<grid_for(total, 192), 192, 0, st>>>(h1, w, bias, h2, B, H, W);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st) {
+  const long long total = (long long)B * 4 * H * W * (C / 8);
+  upsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, out, B, H, W, C);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_fill_f32(float* p, float v, long long n, cudaStream_t st) {
+  fill_kernel<<<grid_for(n, 256), 256, 0, st>>>(p, v, n);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_f32_to_f32_tap(const void* src, int is_bf16, int ld, float* dst, long long rows, int cols, cudaStream_t st) {
+  tap_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(src, is_bf16, ld, dst, rows, cols);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_add_to_bf16(const float* a, const float* b, bf16* out, long long N, cudaStream_t st) {
+  add_to_bf16_kernel<<<grid_for(N * kCp, 256), 256, 0, st>>>(a, b, out, N);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_sca_stats(const float* x, PadGeom g, float* cavg, float* cmax, float* part_sum, float* part_max, int nparts, cudaStream_t st) {
+  dim3 grid(nparts, g.B);
+  sca_stats_kernel<<<grid, 256, 0, st>>>(x, g, cavg, cmax, part_sum, part_max, nparts);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_sca_mlp(const float* part_sum, const float* part_max, int nparts, PadGeom g, CasaW w, float* s1, float* s2, cudaStream_t st) {
+  sca_mlp_kernel<<<g.B, 192, 0, st>>>(part_sum, part_max, nparts, g, w, s1, s2);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, const float* cmax, const float* s1, const float* s2, CasaW w, bf16* t,
+                     cudaStream_t st) {
+  const long long total = (long long)g.B * g.Hp * g.Wp * (kCp / 8);
+  qkv_build_kernel<<<grid_for(total, 192), 192, 0, st>>>(x, g, casa, cavg, cmax, s1, s2, w, t);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_ua_stats(const float* a, const float* b, int B, int H, int W, float* cavg, float* cmax, float* havg, float* hmax, float* wavg, float* wmax,
+                    cudaStream_t st) {
+  ua_rows_kernel<<<B * H, 192, 0, st>>>(a, b, B, H, W, cavg, cmax, wavg, wmax);
+  HITSIR_CHECK(cudaGetLastError());
+  ua_cols_kernel<<<B * W, 192, 0, st>>>(a, b, B, H, W, havg, hmax);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_ua_small_convs(int B, int H, int W, UaW w, const float* cavg, const float* cmax, const float* havg, const float* hmax, const float* wavg,
+                          const float* wmax, float* c_att, float* h_att, float* w_att, cudaStream_t st) {
+  const long long total = (long long)B * H * W + (long long)B * kC * W + (long long)B * kC * H;
+  ua_small_convs_kernel<<<grid_for(total, 256), 256, 0, st>>>(B, H, W, w, cavg, cmax, havg, hmax, wavg, wmax, c_att, h_att, w_att);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_ua_build(int B, int H, int W, const float* c_att, const float* h_att, const float* w_att, bf16* s, cudaStream_t st) {
+  const long long total = (long long)B * H * W * kCp;
+  ua_build_kernel<<<grid_for(total, 256), 256, 0, st>>>(B, H, W, c_att, h_att, w_att, s);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_fusion_combine(const float* first, const float* second, const float* a1, const float* a2, const float* a3, bf16* out, float* of, long long N,
+                          cudaStream_t st) {
+  fusion_combine_kernel<<<grid_for(N * kCp, 256), 256, 0, st>>>(first, second, a1, a2, a3, out, of, N);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hitsir

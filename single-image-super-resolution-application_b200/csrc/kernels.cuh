@@ -1,0 +1,106 @@
+// Launch prototypes of the non-GEMM kernels (glue.cu, scc.cu, pack.cu).
+#pragma once
+#include "common.cuh"
+
+namespace hitsir {
+
+constexpr int kC = 180;        // embedding width of HiT-SIR-pro
+constexpr int kCp = 192;       // padded to a multiple of 64 for TMA / UMMA K blocks
+constexpr int kHalf = 90;      // q | v split (hit_sir_pro.py:569-570)
+constexpr int kHeads = 6;
+constexpr int kHd = 15;        // head dim = C / (2*heads)
+constexpr int kHid = 360;      // ConvFFN hidden width (mlp_ratio 2)
+constexpr int kHidp = 384;
+
+// ---- glue.cu ---------------------------------------------------------------------------
+// NCHW fp32 image -> im2col rows [N, Kp] bf16 of ((x - mean) * img_range), footprint f x f, zero padded
+int launch_entry_im2col(const float* x, bf16* a0, int B, int H, int W, int in_ch, int f, int Kp,
+                        const float* mean3, float img_range, cudaStream_t st);
+// LayerNorm over rows of fp32 [N,180] -> bf16 [N,192] (pad zero) and/or fp32 [N,180]
+int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* out_bf16, float* out_f32, long long N, cudaStream_t st);
+// depthwise 5x5 (zero pad 2) + bias -> GELU -> + input  (ConvFFN middle, hit_sir_pro.py:42)
+int launch_dwconv5_gelu_add(const bf16* h1, const float* w_tap_major, const float* bias, bf16* h2, int B, int H, int W, cudaStream_t st);
+// nearest x2 upsample of an NHWC bf16 map with C channels
+int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st);
+int launch_fill_f32(float* p, float v, long long n, cudaStream_t st);
+int launch_f32_to_f32_tap(const void* src, int src_is_bf16, int ld_src, float* dst, long long rows, int cols, cudaStream_t st);
+// out_bf16[N,192] = bf16(a + b) (fusion disabled path, hit_sir_pro.py:1153)
+int launch_add_to_bf16(const float* a, const float* b, bf16* out, long long N, cudaStream_t st);
+
+// ---- casa (SpatialChannelAttention, hit_sir_pro.py:338-359) ------------------------------
+struct CasaW {
+  const float* w1; const float* b1;      // linear1: Conv2d(1,C,3) as [9][C], [C]
+  const float* w2; const float* b2;      // linear2
+  const float* l1f_w; const float* l1f_b;   // [18][180], [18]
+  const float* l1s_w; const float* l1s_b;   // [180][18], [180]
+  const float* l2f_w; const float* l2f_b;
+  const float* l2s_w; const float* l2s_b;
+};
+struct PadGeom {
+  int B, H, W, Hp, Wp;     // real and reflect-padded sizes
+};
+// per padded pixel channel mean / max + deterministic per-image per-channel (sum, max) partials
+int launch_sca_stats(const float* x, PadGeom g, float* cavg, float* cmax, float* part_sum, float* part_max, int nparts, cudaStream_t st);
+int launch_sca_mlp(const float* part_sum, const float* part_max, int nparts, PadGeom g, CasaW w, float* s1, float* s2, cudaStream_t st);
+// t[b,yp,xp,:] = x[reflect src] (+ casa gate)  -> bf16 [B*Hp*Wp, 192]
+int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, const float* cmax, const float* s1, const float* s2,
+                     CasaW w, bf16* t, cudaStream_t st);
+
+// ---- scc.cu (SCC.forward without proj, hit_sir_pro.py:542-596) --------------------------------
+struct SccW {
+  const float* wk1; const float* bk1;    // k_generate1 [15][15], [15]
+  const float* wk2; const float* bk2;    // k_generate2
+  const float* wsl; float* bsl_dev;      // spatial_linear weight [r*r]; bias read from device (1 float)
+  const float* bias_tbl;                 // pooled relative-position bias [6][L][Lb]
+};
+struct SccGeom {
+  PadGeom pg;
+  int w, base, r;      // window, pooled grid side (min(w,8)), w/base
+  int L, Lb;
+  int nWy, nWx;        // windows per image
+  int parts;           // CTAs per window in the two-phase path (L / 256), 1 for the fused path
+};
+int scc_workspace_floats(const SccGeom& g, long long* partial_floats, long long* final_floats);
+int launch_scc(const bf16* t, const SccGeom& g, const SccW& w, float* partials, float* finals, bf16* out, cudaStream_t st);
+
+// ---- fusion (UnionAttention / Fusion, hit_sir_pro.py:104-162) -------------------------------------
+struct UaW {
+  const float* c1_w; const float* c1_b;   // conv1 [1][2][3][3], [1]
+  const float* c2_w; const float* c2_b;
+  const float* c3_w; const float* c3_b;
+};
+// stats of X = a (+ b if b != nullptr) over channels / rows / columns
+int launch_ua_stats(const float* a, const float* b, int B, int H, int W,
+                    float* cavg, float* cmax,        // [B,H,W]
+                    float* havg, float* hmax,        // [B,C,W]  (reduced over H)
+                    float* wavg, float* wmax,        // [B,C,H]  (reduced over W)
+                    cudaStream_t st);
+int launch_ua_small_convs(int B, int H, int W, UaW w, const float* cavg, const float* cmax, const float* havg, const float* hmax,
+                          const float* wavg, const float* wmax, float* c_att, float* h_att, float* w_att, cudaStream_t st);
+// S[n, c] = c_att[y,x] + w_att[c,y] + h_att[c,x]  -> bf16 [N,192]
+int launch_ua_build(int B, int H, int W, const float* c_att, const float* h_att, const float* w_att, bf16* s, cudaStream_t st);
+// out = first*sigmoid(a1*sigmoid(a2)) + second*sigmoid(a3*(1-sigmoid(a2)))  -> bf16 [N,192] (+ fp32 tap)
+int launch_fusion_combine(const float* first, const float* second, const float* a1, const float* a2, const float* a3,
+                          bf16* out, float* out_f32, long long N, cudaStream_t st);
+
+// ---- pack.cu (weight-only precomputation) --------------------------------------------------------
+// conv / linear weight fp32 [Co][Ci][kh][kw] -> bf16 [Npad][taps*Cipad], k = tap*Cipad + ci; bias -> fp32 [Npad]
+int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, cudaStream_t st);
+// MultipleSizeConvExtract: conv3/5/7/9 + conv_x embedded in a 9x9x3 footprint, rows grouped per 36 channels (EPI_MSGATE)
+int launch_pack_msconv(const float* w3, const float* w5, const float* w7, const float* w9, const float* wx,
+                       const float* b3, const float* b5, const float* b7, const float* b9, const float* bx,
+                       bf16* wp, float* bp, int in_ch, int Kp, cudaStream_t st);
+// first-layer plain conv (f x f footprint over in_ch) -> [192][Kp] with k = (ky*f+kx)*in_ch + ci
+int launch_pack_firstconv(const float* w, const float* b, bf16* wp, float* bp, int Co, int in_ch, int f, int Kp, cudaStream_t st);
+// [C][1][kh][kw] -> [kh*kw][Cpad] fp32 (tap major); used for depthwise 5x5 (C=360->384) and casa 3x3 (1->C)
+int launch_pack_tapmajor(const float* w, float* out, int C, int taps, int Cpad, cudaStream_t st);
+struct PosW {
+  const float* proj_w; const float* proj_b;   // [11][2], [11]
+  const float* ln_w[3]; const float* ln_b[3]; // [11] x3
+  const float* fc_w[3]; const float* fc_b[3]; // [11][11],[11][11],[6][11]
+};
+// DynamicPosBias MLP over all (2w-1)^2 offsets -> tbl [(2w-1)^2][6]; then pooled bias [6][L][Lb]
+int launch_pos_table(PosW w, int win, float* tbl, cudaStream_t st);
+int launch_pooled_bias(const float* tbl, int win, int base, float* out, cudaStream_t st);
+
+}  // namespace hitsir

@@ -1,0 +1,176 @@
+// Weight-only precomputation, run once per weight load (never in the forward):
+//   * fp32 nn.Linear / nn.Conv2d tensors -> bf16 K-major GEMM operands padded for TMA/UMMA;
+//   * the DynamicPosBias MLP table and its pooled relative-position bias (hit_sir_pro.py:477-503),
+//     which the reference rebuilds on every forward of every block although it only depends on weights.
+#include "kernels.cuh"
+
+namespace hitsir {
+
+namespace {
+
+inline int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  return (int)(g < 4096 ? (g > 0 ? g : 1) : 4096);
+}
+
+__global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp, float* __restrict__ bp,
+                                 int Co, int Ci, int taps, int Npad, int Cipad) {
+  const long long K = (long long)taps * Cipad;
+  const long long total = (long long)Npad * K;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / K); const int k = (int)(idx - (long long)n * K);
+    const int tap = k / Cipad, ci = k - tap * Cipad;
+    float v = 0.f;
+    if (n < Co && ci < Ci) v = w[((long long)n * Ci + ci) * taps + tap];     // [Co][Ci][kh][kw], tap = kh*kw_size + kw
+    wp[idx] = __float2bfloat16(v);
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < Npad; n += gridDim.x * blockDim.x) bp[n] = (n < Co && b != nullptr) ? b[n] : 0.f;
+}
+
+// rows: tile j (0..4) x [slot q (0..4: conv3,5,7,9,conv_x) x 36 channels] (+12 zero rows); K = 9x9 footprint x in_ch
+__global__ void pack_msconv_kernel(const float* __restrict__ w3, const float* __restrict__ w5, const float* __restrict__ w7, const float* __restrict__ w9,
+                                   const float* __restrict__ wx, const float* __restrict__ b3, const float* __restrict__ b5, const float* __restrict__ b7,
+                                   const float* __restrict__ b9, const float* __restrict__ bx, bf16* __restrict__ wp, float* __restrict__ bp, int in_ch, int Kp) {
+  const long long total = 960LL * Kp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / Kp), k = (int)(idx - (long long)n * Kp);
+    const int j = n / 192, rem = n - j * 192;
+    float v = 0.f;
+    if (rem < 180 && k < 81 * in_ch) {
+      const int q = rem / 36, c = 36 * j + (rem - q * 36);
+      const int tap = k / in_ch, ci = k - tap * in_ch;
+      const int ky = tap / 9, kx = tap - ky * 9;
+      const int s = (q < 4) ? (3 + 2 * q) : 1;        // filter size
+      const int off = (9 - s) / 2;
+      const int fy = ky - off, fx = kx - off;
+      if (fy >= 0 && fy < s && fx >= 0 && fx < s) {
+        const float* src = q == 0 ? w3 : q == 1 ? w5 : q == 2 ? w7 : q == 3 ? w9 : wx;
+        v = src[(((long long)c * in_ch + ci) * s + fy) * s + fx];
+      }
+    }
+    wp[idx] = __float2bfloat16(v);
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < 960; n += gridDim.x * blockDim.x) {
+    const int j = n / 192, rem = n - j * 192;
+    float v = 0.f;
+    if (rem < 180) {
+      const int q = rem / 36, c = 36 * j + (rem - q * 36);
+      const float* src = q == 0 ? b3 : q == 1 ? b5 : q == 2 ? b7 : q == 3 ? b9 : bx;
+      v = src[c];
+    }
+    bp[n] = v;
+  }
+}
+
+__global__ void pack_firstconv_kernel(const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp, float* __restrict__ bp,
+                                      int Co, int in_ch, int f, int Kp) {
+  const long long total = 192LL * Kp;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / Kp), k = (int)(idx - (long long)n * Kp);
+    float v = 0.f;
+    if (n < Co && k < f * f * in_ch) {
+      const int tap = k / in_ch, ci = k - tap * in_ch;
+      v = w[((long long)n * in_ch + ci) * f * f + tap];
+    }
+    wp[idx] = __float2bfloat16(v);
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < 192; n += gridDim.x * blockDim.x) bp[n] = n < Co ? b[n] : 0.f;
+}
+
+__global__ void pack_tapmajor_kernel(const float* __restrict__ w, float* __restrict__ out, int C, int taps, int Cpad) {
+  const int total = taps * Cpad;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int tap = idx / Cpad, c = idx - tap * Cpad;
+    out[idx] = c < C ? w[c * taps + tap] : 0.f;
+  }
+}
+
+__device__ __forceinline__ void ln_relu(float* v, int n, const float* g, const float* b) {
+  float m = 0.f;
+  for (int i = 0; i < n; ++i) m += v[i];
+  m /= (float)n;
+  float q = 0.f;
+  for (int i = 0; i < n; ++i) { const float d = v[i] - m; q += d * d; }
+  const float rstd = rsqrtf(q / (float)n + 1e-5f);
+  for (int i = 0; i < n; ++i) v[i] = fmaxf((v[i] - m) * rstd * g[i] + b[i], 0.f);
+}
+
+// DynamicPosBias (residual=False): Linear 2->11, then 3 x (LayerNorm, ReLU, Linear); (:305-313)
+__global__ void pos_table_kernel(PosW w, int win, float* __restrict__ tbl) {
+  constexpr int D = 11;
+  const int side = 2 * win - 1;
+  const int total = side * side;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const float dy = (float)(idx / side - (win - 1)), dx = (float)(idx % side - (win - 1));
+    float a[D], t[D];
+    for (int o = 0; o < D; ++o) a[o] = w.proj_w[o * 2] * dy + w.proj_w[o * 2 + 1] * dx + w.proj_b[o];
+    for (int s = 0; s < 2; ++s) {
+      ln_relu(a, D, w.ln_w[s], w.ln_b[s]);
+      for (int o = 0; o < D; ++o) { float acc = w.fc_b[s][o]; for (int i = 0; i < D; ++i) acc += w.fc_w[s][o * D + i] * a[i]; t[o] = acc; }
+      for (int o = 0; o < D; ++o) a[o] = t[o];
+    }
+    ln_relu(a, D, w.ln_w[2], w.ln_b[2]);
+    for (int o = 0; o < kHeads; ++o) {
+      float acc = w.fc_b[2][o];
+      for (int i = 0; i < D; ++i) acc += w.fc_w[2][o * D + i] * a[i];
+      tbl[idx * kHeads + o] = acc;
+    }
+  }
+}
+
+// bias[h][l][cell] = mean over the r x r tokens m of the cell of tbl[(yl-ym+w-1)*(2w-1) + (xl-xm+w-1)][h]   (:486-501)
+__global__ void pooled_bias_kernel(const float* __restrict__ tbl, int win, int base, float* __restrict__ out) {
+  const int r = win / base, L = win * win, Lb = base * base, side = 2 * win - 1;
+  const long long total = (long long)kHeads * L * Lb;
+  const float inv = 1.0f / (float)(r * r);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cell = (int)(idx % Lb); const long long t = idx / Lb; const int l = (int)(t % L); const int h = (int)(t / L);
+    const int yl = l / win, xl = l - yl * win;
+    const int cy = cell / base, cx = cell - cy * base;
+    float s = 0.f;
+    for (int i = 0; i < r; ++i)
+      for (int j = 0; j < r; ++j) {
+        const int ym = cy * r + i, xm = cx * r + j;
+        s += tbl[((yl - ym + win - 1) * side + (xl - xm + win - 1)) * kHeads + h];
+      }
+    out[idx] = s * inv;
+  }
+}
+
+}  // namespace
+
+int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, cudaStream_t st) {
+  pack_conv_kernel<<<grid_for((long long)Npad * taps * Cipad, 256), 256, 0, st>>>(w, b, wp, bp, Co, Ci, taps, Npad, Cipad);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pack_msconv(const float* w3, const float* w5, const float* w7, const float* w9, const float* wx, const float* b3, const float* b5,
+                       const float* b7, const float* b9, const float* bx, bf16* wp, float* bp, int in_ch, int Kp, cudaStream_t st) {
+  pack_msconv_kernel<<<grid_for(960LL * Kp, 256), 256, 0, st>>>(w3, w5, w7, w9, wx, b3, b5, b7, b9, bx, wp, bp, in_ch, Kp);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pack_firstconv(const float* w, const float* b, bf16* wp, float* bp, int Co, int in_ch, int f, int Kp, cudaStream_t st) {
+  pack_firstconv_kernel<<<grid_for(192LL * Kp, 256), 256, 0, st>>>(w, b, wp, bp, Co, in_ch, f, Kp);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pack_tapmajor(const float* w, float* out, int C, int taps, int Cpad, cudaStream_t st) {
+  pack_tapmajor_kernel<<<grid_for((long long)taps * Cpad, 256), 256, 0, st>>>(w, out, C, taps, Cpad);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pos_table(PosW w, int win, float* tbl, cudaStream_t st) {
+  const int total = (2 * win - 1) * (2 * win - 1);
+  pos_table_kernel<<<grid_for(total, 128), 128, 0, st>>>(w, win, tbl);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pooled_bias(const float* tbl, int win, int base, float* out, cudaStream_t st) {
+  const long long total = (long long)kHeads * win * win * base * base;
+  pooled_bias_kernel<<<grid_for(total, 256), 256, 0, st>>>(tbl, win, base, out);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hitsir
