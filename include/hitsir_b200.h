@@ -118,6 +118,13 @@ HITSIR_API int hitsir_set_tap(HitsirHandle* h, const char* name, float* dst, int
 /* Number of kernels the last hitsir_forward launched (bench.py's gpu_launches). */
 HITSIR_API int64_t hitsir_last_launch_count(const HitsirHandle* h);
 
+/* Per-category CUDA-event timing of the launches inside hitsir_forward (events on the caller's stream, no
+ * synchronisation added).  Enable, run forwards, synchronise the stream yourself, then read the totals
+ * accumulated since the last hitsir_profile_enable call.  Used by bench.py for the live roofline numbers. */
+HITSIR_API int hitsir_profile_enable(HitsirHandle* h, int on);
+HITSIR_API int hitsir_profile_num_categories(const HitsirHandle* h);
+HITSIR_API int hitsir_profile_get(HitsirHandle* h, int index, const char** name, double* total_ms, int64_t* launches);
+
 /* "umma" (tcgen05 path, default) or "simt" (cross-check kernels); also via env HITSIR_GEMM. */
 HITSIR_API int hitsir_set_gemm_backend(HitsirHandle* h, const char* backend);
 

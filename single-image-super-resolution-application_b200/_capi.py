@@ -54,6 +54,9 @@ SYMBOLS = {
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "hitsir_set_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int]),
     "hitsir_last_launch_count": (C.c_int64, [C.c_void_p]),
+    "hitsir_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
+    "hitsir_profile_num_categories": (C.c_int, [C.c_void_p]),
+    "hitsir_profile_get": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     "hitsir_set_gemm_backend": (C.c_int, [C.c_void_p, C.c_char_p]),
     "hitsir_last_error": (C.c_char_p, []),
     "hitsir_version": (C.c_char_p, []),

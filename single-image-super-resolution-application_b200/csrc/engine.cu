@@ -54,6 +54,24 @@ struct UaPack {
   GemmW conv_last;
 };
 
+// optional per-category CUDA-event timing of the launches of a forward (bench.py's live roofline numbers)
+struct ProfRec { int cat; cudaEvent_t a, b; };
+struct Prof {
+  bool on = false;
+  std::vector<std::string> cats;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;   // recycled events
+  int cat_id(const char* name) {
+    for (size_t i = 0; i < cats.size(); ++i) if (cats[i] == name) return (int)i;
+    cats.push_back(name);
+    return (int)cats.size() - 1;
+  }
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+
 struct Tap {
   std::string name;
   float* dst = nullptr;
@@ -89,6 +107,7 @@ struct HitsirHandle {
   // per-forward state
   Tap tap;
   int64_t launches = 0;
+  Prof prof;
 };
 
 namespace {
@@ -523,11 +542,24 @@ int do_tap(Fwd& f, const char* name, const void* src, int is_bf16, int ld, long 
   if (t.dst == nullptr || t.name != name) return 0;
   if (rows * cols > t.floats) { set_error("tap '%s' needs %lld floats, destination has %lld", name, rows * cols, (long long)t.floats); return HITSIR_ERR_INVALID; }
   if (launch_f32_to_f32_tap(src, is_bf16, ld, t.dst, rows, cols, f.st)) return 1;
-  f.h->launches++;
   if (t.stop) f.stopped = true;
   return 0;
 }
 
+#define RUN(expr) do { int _r = (expr); if (_r) return _r; } while (0)
+struct ProfScope {
+  HitsirHandle* h; cudaStream_t st; int idx = -1;
+  ProfScope(HitsirHandle* h_, cudaStream_t st_, const char* cat) : h(h_), st(st_) {
+    if (!h->prof.on) return;
+    ProfRec r{h->prof.cat_id(cat), h->prof.get(), h->prof.get()};
+    cudaEventRecord(r.a, st);
+    h->prof.recs.push_back(r);
+    idx = (int)h->prof.recs.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(h->prof.recs[idx].b, st); }
+};
+// one (or n) kernel launch(es) of category `cat`
+#define LAUNCH(cat, n, expr) do { ProfScope _ps(f.h, f.st, cat); f.h->launches += (n); int _r = (expr); if (_r) return _r; } while (0)
 void base_params(GemmParams& p, const GemmW& w) {
   memset(&p, 0, sizeof(p));
   p.n_tiles = w.Npad / w.BN;
@@ -539,23 +571,24 @@ void base_params(GemmParams& p, const GemmW& w) {
   p.slope = 1.f;
 }
 
-int run_gemm(Fwd& f, const GemmW& w, GemmParams& p, const CUtensorMap& ta) {
+int run_gemm(Fwd& f, const char* cat, const GemmW& w, GemmParams& p, const CUtensorMap& ta) {
+  ProfScope ps(f.h, f.st, cat);
   f.h->launches++;
   if (f.h->simt) return launch_simt_gemm(w.BN, p, f.st);
   return launch_umma_gemm(w.BN, p, ta, w.tm, f.h->num_sms, f.st);
 }
 
 // token-major linear: A [M, lda] bf16 (lda == w.K)
-int linear(Fwd& f, const GemmW& w, const bf16* A, long long M, GemmParams& p) {
+int linear(Fwd& f, const char* cat, const GemmW& w, const bf16* A, long long M, GemmParams& p) {
   p.conv = 0; p.M = (int)M; p.m_tiles = (int)cdiv64(M, 128);
   p.A = A; p.lda = w.K;
   CUtensorMap ta;
   if (!f.h->simt && make_tmap_2d(&ta, A, (uint64_t)w.K, (uint64_t)M, (uint64_t)w.K * 2, 64, 128)) return 1;
-  return run_gemm(f, w, p, ta);
+  return run_gemm(f, cat, w, p, ta);
 }
 
 // 3x3 conv over NHWC bf16 [B,H,W,Cpad]
-int conv3(Fwd& f, const GemmW& w, const bf16* A, int B, int H, int W, int Cpad, GemmParams& p) {
+int conv3(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, int W, int Cpad, GemmParams& p) {
   p.conv = 1; p.B = B; p.H = H; p.W = W;
   p.tiles_x = cdiv(W, 16); p.tiles_y = cdiv(H, 8);
   p.m_tiles = B * p.tiles_x * p.tiles_y;
@@ -564,10 +597,9 @@ int conv3(Fwd& f, const GemmW& w, const bf16* A, int B, int H, int W, int Cpad, 
   if (w.K != 9 * Cpad) { set_error("conv3: packed K %d != 9*%d", w.K, Cpad); return 1; }
   CUtensorMap ta;
   if (!f.h->simt && make_tmap_nhwc(&ta, A, B, H, W, Cpad, 64, 16, 8)) return 1;
-  return run_gemm(f, w, p, ta);
+  return run_gemm(f, cat, w, p, ta);
 }
 
-#define RUN(expr) do { int _r = (expr); if (_r) return _r; } while (0)
 #define TAP(name, src, is_bf16, ld, rows, cols) do { RUN(do_tap(f, name, src, is_bf16, ld, rows, cols)); if (f.stopped) return 0; } while (0)
 
 int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
@@ -584,30 +616,30 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   g.nWy = g.pg.Hp / w; g.nWx = g.pg.Wp / w; g.parts = scc_parts(g.L);
   const long long Np = (long long)f.B * g.pg.Hp * g.pg.Wp;
   if (c.is_channel_spatial_attn) {
-    RUN(launch_sca_stats(xin, g.pg, ws.cavg, ws.cmax, ws.part_sum, ws.part_max, ws.nparts, f.st)); h->launches++;
-    RUN(launch_sca_mlp(ws.part_sum, ws.part_max, ws.nparts, g.pg, bw.casa, ws.s1, ws.s2, f.st)); h->launches++;
+    LAUNCH("sca_stats", 1, launch_sca_stats(xin, g.pg, ws.cavg, ws.cmax, ws.part_sum, ws.part_max, ws.nparts, f.st));
+    LAUNCH("sca_mlp", 1, launch_sca_mlp(ws.part_sum, ws.part_max, ws.nparts, g.pg, bw.casa, ws.s1, ws.s2, f.st));
   }
-  RUN(launch_qkv_build(xin, g.pg, c.is_channel_spatial_attn, ws.cavg, ws.cmax, ws.s1, ws.s2, bw.casa, ws.T, f.st)); h->launches++;
+  LAUNCH("qkv_build", 1, launch_qkv_build(xin, g.pg, c.is_channel_spatial_attn, ws.cavg, ws.cmax, ws.s1, ws.s2, bw.casa, ws.T, f.st));
   TAP((tn + ".qkv").c_str(), ws.T, 1, kCp, Np, kC);
-  RUN(launch_scc(ws.T, g, bw.scc, ws.scc_part, ws.scc_fin, ws.outsc, f.st)); h->launches += (g.parts > 1 ? 3 : 1);
+  { char cat[16]; snprintf(cat, sizeof(cat), "scc_w%d", w); LAUNCH(cat, (g.parts > 1 ? 3 : 1), launch_scc(ws.T, g, bw.scc, ws.scc_part, ws.scc_fin, ws.outsc, f.st)); }
   TAP((tn + ".scc").c_str(), ws.outsc, 1, kCp, f.N, kC);
   GemmParams p;
   // proj + norm1 + residual (:597, :700-703)
   base_params(p, bw.proj);
   p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g1; p.beta = bw.b1; p.res = xin; p.ldr = kC;
   p.out_f32 = xout; p.ldf = kC; p.out_bf16 = ws.xb0; p.ldb = kCp;
-  RUN(linear(f, bw.proj, ws.outsc, f.N, p));
+  RUN(linear(f, "gemm_proj_ln", bw.proj, ws.outsc, f.N, p));
   TAP((tn + ".attn").c_str(), xout, 0, kC, f.N, kC);
   // ConvFFN (:39-46): fc1 + GELU
   base_params(p, bw.fc1);
   p.epi = EPI_STORE; p.act = ACT_GELU; p.n_real = kHid; p.out_bf16 = ws.H1; p.ldb = kHidp;
-  RUN(linear(f, bw.fc1, ws.xb0, f.N, p));
-  RUN(launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, f.st)); h->launches++;
+  RUN(linear(f, "gemm_fc1_gelu", bw.fc1, ws.xb0, f.N, p));
+  LAUNCH("dwconv5", 1, launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, f.st));
   // fc2 + norm2 + residual (:704)
   base_params(p, bw.fc2);
   p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g2; p.beta = bw.b2; p.res = xout; p.ldr = kC;
   p.out_f32 = xout; p.ldf = kC; p.out_bf16 = ws.xb0; p.ldb = kCp;
-  RUN(linear(f, bw.fc2, ws.H2, f.N, p));
+  RUN(linear(f, "gemm_fc2_ln", bw.fc2, ws.H2, f.N, p));
   TAP(tn.c_str(), xout, 0, kC, f.N, kC);
   return 0;
 }
@@ -616,14 +648,13 @@ int union_attention(Fwd& f, int u, const float* a, const float* b, float* out) {
   // UnionAttention.forward (:113-133) on X = a (+ b)
   HitsirHandle* h = f.h;
   Workspace& ws = f.ws;
-  RUN(launch_ua_stats(a, b, f.B, f.H, f.W, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, f.st)); h->launches += 2;
-  RUN(launch_ua_small_convs(f.B, f.H, f.W, h->ua[u].small, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, ws.c_att, ws.h_att, ws.w_att, f.st));
-  h->launches++;
-  RUN(launch_ua_build(f.B, f.H, f.W, ws.c_att, ws.h_att, ws.w_att, ws.outsc, f.st)); h->launches++;
+  LAUNCH("ua_stats", 2, launch_ua_stats(a, b, f.B, f.H, f.W, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, f.st));
+  LAUNCH("ua_small", 1, launch_ua_small_convs(f.B, f.H, f.W, h->ua[u].small, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, ws.c_att, ws.h_att, ws.w_att, f.st));
+  LAUNCH("ua_build", 1, launch_ua_build(f.B, f.H, f.W, ws.c_att, ws.h_att, ws.w_att, ws.outsc, f.st));
   GemmParams p;
   base_params(p, h->ua[u].conv_last);
   p.epi = EPI_STORE; p.n_real = kC; p.out_f32 = out; p.ldf = kC;
-  return conv3(f, h->ua[u].conv_last, ws.outsc, f.B, f.H, f.W, kCp, p);
+  return conv3(f, "conv_ua", h->ua[u].conv_last, ws.outsc, f.B, f.H, f.W, kCp, p);
 }
 
 int forward_impl(Fwd& f, const float* x, float* y) {
@@ -635,24 +666,24 @@ int forward_impl(Fwd& f, const float* x, float* y) {
   GemmParams p;
   // ---- mean shift + shallow features (:1310-1311, :1315/1322/1328/1337) + patch_embed LayerNorm (:975-983)
   bf16* A0 = ws.xb0;   // [N, first_kp <= 384] aliases xb0|xb1, dead before the second GEMM writes xb0
-  RUN(launch_entry_im2col(x, A0, B, H, W, c.in_chans, h->first_f, h->first_kp, h->mean, c.img_range, f.st)); h->launches++;
+  LAUNCH("im2col", 1, launch_entry_im2col(x, A0, B, H, W, c.in_chans, h->first_f, h->first_kp, h->mean, c.img_range, f.st));
   const float* pe_g = P(h, "patch_embed.norm.weight");
   const float* pe_b = P(h, "patch_embed.norm.bias");
   if (c.is_mult_size_conv_feat_extract) {
     bf16* G = ws.H1;   // [N,768] aliases H1|H2
     base_params(p, h->first);
     p.epi = EPI_MSGATE; p.n_real = kC; p.out_bf16 = G; p.ldb = 4 * kCp;
-    RUN(linear(f, h->first, A0, N, p));
+    RUN(linear(f, "gemm_first_msgate", h->first, A0, N, p));
     base_params(p, h->first_last);
     p.epi = EPI_LN; p.n_real = kC; p.gamma = pe_g; p.beta = pe_b;
     p.out2_f32 = ws.S; p.ldf2 = kC; p.out_f32 = ws.P; p.ldf = kC;
-    RUN(linear(f, h->first_last, G, N, p));
+    RUN(linear(f, "gemm_first_last_ln", h->first_last, G, N, p));
   } else {
     // the plain conv_first reads A0 (in xb0|xb1) so it must not write a bf16 shadow there
     base_params(p, h->first);
     p.epi = EPI_LN; p.n_real = kC; p.gamma = pe_g; p.beta = pe_b;
     p.out2_f32 = ws.S; p.ldf2 = kC; p.out_f32 = ws.P; p.ldf = kC;
-    RUN(linear(f, h->first, A0, N, p));
+    RUN(linear(f, "gemm_first_ln", h->first, A0, N, p));
   }
   TAP("shallow", ws.S, 0, kC, N, kC);
   TAP("embed", ws.P, 0, kC, N, kC);
@@ -664,16 +695,16 @@ int forward_impl(Fwd& f, const float* x, float* y) {
     }
     base_params(p, h->layer_conv[i]);
     p.epi = EPI_STORE; p.n_real = kC; p.res = ws.P; p.ldr = kC; p.out_f32 = ws.P; p.ldf = kC;
-    RUN(conv3(f, h->layer_conv[i], ws.xb0, B, H, W, kCp, p));
+    RUN(conv3(f, "conv_layer", h->layer_conv[i], ws.xb0, B, H, W, kCp, p));
     TAP(("layer" + std::to_string(i)).c_str(), ws.P, 0, kC, N, kC);
   }
   // ---- final norm + conv_after_body (:1299-1300, :1317/1324/1330/1339)
-  RUN(launch_ln_rows(ws.P, P(h, "norm.weight"), P(h, "norm.bias"), ws.xb0, nullptr, N, f.st)); h->launches++;
+  LAUNCH("ln_rows", 1, launch_ln_rows(ws.P, P(h, "norm.weight"), P(h, "norm.bias"), ws.xb0, nullptr, N, f.st));
   TAP("norm", ws.xb0, 1, kCp, N, kC);
   float* CAB = ws.Q;
   base_params(p, h->conv_after_body);
   p.epi = EPI_STORE; p.n_real = kC; p.out_f32 = CAB; p.ldf = kC;
-  RUN(conv3(f, h->conv_after_body, ws.xb0, B, H, W, kCp, p));
+  RUN(conv3(f, "conv_after_body", h->conv_after_body, ws.xb0, B, H, W, kCp, p));
   TAP("conv_after_body", CAB, 0, kC, N, kC);
   // ---- fusion(conv_after_body(deep), shallow): positional binding (:1330 -> :145)
   bf16* F = ws.xb1;
@@ -686,10 +717,10 @@ int forward_impl(Fwd& f, const float* x, float* y) {
     RUN(union_attention(f, 2, ws.S, nullptr, A3));
     float* tapdst = (h->tap.dst != nullptr && h->tap.name == "fused") ? h->tap.dst : nullptr;
     if (tapdst != nullptr && N * kC > h->tap.floats) { set_error("tap 'fused' destination too small"); return HITSIR_ERR_INVALID; }
-    RUN(launch_fusion_combine(CAB, ws.S, A1, A2, A3, F, tapdst, N, f.st)); h->launches++;
+    LAUNCH("fusion_combine", 1, launch_fusion_combine(CAB, ws.S, A1, A2, A3, F, tapdst, N, f.st));
     if (tapdst != nullptr && h->tap.stop) { f.stopped = true; return 0; }
   } else {
-    RUN(launch_add_to_bf16(CAB, ws.S, F, N, f.st)); h->launches++;
+    LAUNCH("fusion_add", 1, launch_add_to_bf16(CAB, ws.S, F, N, f.st));
     TAP("fused", F, 1, kCp, N, kC);
   }
   // ---- reconstruction (:1313-1340)
@@ -710,31 +741,31 @@ int forward_impl(Fwd& f, const float* x, float* y) {
     bf16* U3 = U1up;
     base_params(p, h->conv_before_upsample);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.01f; p.n_real = kNumFeat; p.out_bf16 = U0; p.ldb = kNumFeat;   // nn.LeakyReLU() default slope (:1251)
-    RUN(conv3(f, h->conv_before_upsample, F, B, H, W, kCp, p));
+    RUN(conv3(f, "conv_before_upsample", h->conv_before_upsample, F, B, H, W, kCp, p));
     TAP("conv_before_upsample", U0, 1, kNumFeat, N, kNumFeat);
-    RUN(launch_upsample_nearest2(U0, U0up, B, H, W, kNumFeat, f.st)); h->launches++;
+    LAUNCH("upsample2", 1, launch_upsample_nearest2(U0, U0up, B, H, W, kNumFeat, f.st));
     base_params(p, h->conv_up1);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = kNumFeat; p.out_bf16 = U1; p.ldb = kNumFeat;
-    RUN(conv3(f, h->conv_up1, U0up, B, 2 * H, 2 * W, kNumFeat, p));
+    RUN(conv3(f, "conv_up1", h->conv_up1, U0up, B, 2 * H, 2 * W, kNumFeat, p));
     TAP("up1", U1, 1, kNumFeat, 4 * N, kNumFeat);
-    RUN(launch_upsample_nearest2(U1, U1up, B, 2 * H, 2 * W, kNumFeat, f.st)); h->launches++;
+    LAUNCH("upsample2", 1, launch_upsample_nearest2(U1, U1up, B, 2 * H, 2 * W, kNumFeat, f.st));
     base_params(p, h->conv_up2);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = kNumFeat; p.out_bf16 = U2; p.ldb = kNumFeat;
-    RUN(conv3(f, h->conv_up2, U1up, B, 4 * H, 4 * W, kNumFeat, p));
+    RUN(conv3(f, "conv_up2", h->conv_up2, U1up, B, 4 * H, 4 * W, kNumFeat, p));
     TAP("up2", U2, 1, kNumFeat, 16 * N, kNumFeat);
     base_params(p, h->conv_hr);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = kNumFeat; p.out_bf16 = U3; p.ldb = kNumFeat;
-    RUN(conv3(f, h->conv_hr, U2, B, 4 * H, 4 * W, kNumFeat, p));
+    RUN(conv3(f, "conv_hr", h->conv_hr, U2, B, 4 * H, 4 * W, kNumFeat, p));
     TAP("hr", U3, 1, kNumFeat, 16 * N, kNumFeat);
     last_params(p, h->conv_last, 1);
-    RUN(conv3(f, h->conv_last, U3, B, 4 * H, 4 * W, kNumFeat, p));
+    RUN(conv3(f, "conv_last", h->conv_last, U3, B, 4 * H, 4 * W, kNumFeat, p));
   } else if (c.upsampler == HITSIR_UP_PIXELSHUFFLE) {
     bf16* U0 = ws.up;
     bf16* Ua = U0 + N * kNumFeat;
     bf16* Ub = Ua + 4 * N * kNumFeat;
     base_params(p, h->conv_before_upsample);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.01f; p.n_real = kNumFeat; p.out_bf16 = U0; p.ldb = kNumFeat;
-    RUN(conv3(f, h->conv_before_upsample, F, B, H, W, kCp, p));
+    RUN(conv3(f, "conv_before_upsample", h->conv_before_upsample, F, B, H, W, kCp, p));
     TAP("conv_before_upsample", U0, 1, kNumFeat, N, kNumFeat);
     const bf16* cur = U0;
     int ch = H, cw = W;
@@ -744,20 +775,20 @@ int forward_impl(Fwd& f, const float* x, float* y) {
         if (k >= 2) { set_error("pixelshuffle upscale > 4 not supported by this build"); return HITSIR_ERR_UNSUPPORTED; }
         base_params(p, h->upsample[k]);
         p.epi = EPI_SHUFFLE_BF16; p.ps = 2; p.n_real = 4 * kNumFeat; p.shuf_c = kNumFeat; p.out_bf16 = dst; p.ldb = kNumFeat;
-        RUN(conv3(f, h->upsample[k], cur, B, ch, cw, kNumFeat, p));
+        RUN(conv3(f, "conv_pixelshuffle", h->upsample[k], cur, B, ch, cw, kNumFeat, p));
         cur = dst; ch *= 2; cw *= 2;
       }
     } else {
       base_params(p, h->upsample[0]);
       p.epi = EPI_SHUFFLE_BF16; p.ps = 3; p.n_real = 9 * kNumFeat; p.shuf_c = kNumFeat; p.out_bf16 = Ub; p.ldb = kNumFeat;
-      RUN(conv3(f, h->upsample[0], cur, B, ch, cw, kNumFeat, p));
+      RUN(conv3(f, "conv_pixelshuffle", h->upsample[0], cur, B, ch, cw, kNumFeat, p));
       cur = Ub; ch *= 3; cw *= 3;
     }
     last_params(p, h->conv_last, 1);
-    RUN(conv3(f, h->conv_last, cur, B, ch, cw, kNumFeat, p));
+    RUN(conv3(f, "conv_last", h->conv_last, cur, B, ch, cw, kNumFeat, p));
   } else if (c.upsampler == HITSIR_UP_PIXELSHUFFLEDIRECT) {
     last_params(p, h->upsample[0], s);
-    RUN(conv3(f, h->upsample[0], F, B, H, W, kCp, p));
+    RUN(conv3(f, "conv_last_direct", h->upsample[0], F, B, H, W, kCp, p));
   } else {
     set_error("upsampler=None (x + conv_last(res)) is not implemented in this build");
     return HITSIR_ERR_UNSUPPORTED;
@@ -803,6 +834,8 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
 
 HITSIR_API void hitsir_destroy(HitsirHandle* h) {
   if (!h) return;
+  for (ProfRec& r : h->prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (cudaEvent_t e : h->prof.pool) cudaEventDestroy(e);
   free_owned(h);
   if (h->arena) cudaFree(h->arena);
   delete h;
@@ -882,6 +915,27 @@ HITSIR_API int hitsir_set_tap(HitsirHandle* h, const char* name, float* dst, int
 }
 
 HITSIR_API int64_t hitsir_last_launch_count(const HitsirHandle* h) { return h ? h->launches : 0; }
+
+HITSIR_API int hitsir_profile_enable(HitsirHandle* h, int on) {
+  if (!h) { set_error("null handle"); return HITSIR_ERR_INVALID; }
+  h->prof.on = on != 0;
+  for (ProfRec& r : h->prof.recs) { h->prof.pool.push_back(r.a); h->prof.pool.push_back(r.b); }
+  h->prof.recs.clear();
+  return 0;
+}
+HITSIR_API int hitsir_profile_num_categories(const HitsirHandle* h) { return h ? (int)h->prof.cats.size() : 0; }
+HITSIR_API int hitsir_profile_get(HitsirHandle* h, int i, const char** name, double* total_ms, int64_t* launches) {
+  if (!h || i < 0 || i >= (int)h->prof.cats.size()) { set_error("hitsir_profile_get: bad index"); return HITSIR_ERR_INVALID; }
+  double ms = 0.0; int64_t n = 0;
+  for (const ProfRec& r : h->prof.recs) {
+    if (r.cat != i) continue;
+    float t = 0.f;
+    HITSIR_CHECK(cudaEventElapsedTime(&t, r.a, r.b));
+    ms += t; ++n;
+  }
+  *name = h->prof.cats[i].c_str(); *total_ms = ms; *launches = n;
+  return 0;
+}
 
 HITSIR_API int hitsir_set_gemm_backend(HitsirHandle* h, const char* backend) {
   if (!h || !backend) { set_error("null argument"); return HITSIR_ERR_INVALID; }

@@ -361,6 +361,22 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
         else:
             _capi.check(_capi.load().hitsir_set_tap(h, name.encode(), ctypes.c_void_p(dst.data_ptr()), dst.numel(), int(stop)))
 
+    def profile_enable(self, device, on: bool = True):
+        """Per-category CUDA-event timing of the kernel launches (hitsir_profile_enable); resets the totals."""
+        _capi.check(_capi.load().hitsir_profile_enable(self._handle(torch.device(device)), int(on)))
+
+    def profile_read(self, device) -> Dict[str, tuple]:
+        """{category: (total_ms, launches)} since profile_enable; synchronise the stream first."""
+        lib = _capi.load()
+        h = self._handle(torch.device(device))
+        out = {}
+        for i in range(lib.hitsir_profile_num_categories(h)):
+            name, ms, n = ctypes.c_char_p(), ctypes.c_double(), ctypes.c_int64()
+            _capi.check(lib.hitsir_profile_get(h, i, ctypes.byref(name), ctypes.byref(ms), ctypes.byref(n)))
+            if n.value:
+                out[name.value.decode()] = (ms.value, n.value)
+        return out
+
     def set_gemm_backend(self, device, backend: str):
         _capi.check(_capi.load().hitsir_set_gemm_backend(self._handle(torch.device(device)), backend.encode()))
 

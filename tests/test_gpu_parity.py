@@ -1,0 +1,130 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the public nn.Module -> ctypes -> C ABI, against
+(a) the committed golden vectors of the unmodified reference and (b) the CPU oracle on fresh seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle.weights import synthetic_image
+from tests.helpers import (GOLDEN_CASES, TAP_REL_L2, TOL_MAXABS, TOL_PSNR_DB, build_pair, load_golden, psnr, rel_l2)
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def run_cuda(model, x):
+    model = model.to(DEV)
+    with torch.no_grad():
+        y = model(x.to(DEV))
+    torch.cuda.synchronize()
+    assert model.last_launch_count > 0
+    return y.cpu()
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_cuda_matches_reference_golden(name):
+    g, meta = load_golden(name)
+    model, _ = build_pair(meta["flags"], meta["upsampler"], meta["upscale"], meta["mode"], meta["wseed"])
+    x = synthetic_image(*meta["shape"], seed=meta["xseed"])
+    y = run_cuda(model, x)
+    ref = torch.from_numpy(g["y"])
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert not torch.isnan(y).any()
+    err = (y - ref).abs().max().item()
+    assert err < TOL_MAXABS[meta["mode"]], err
+    assert psnr(y, ref) > TOL_PSNR_DB[meta["mode"]]
+
+
+def test_cuda_taps_match_oracle():
+    """Per-module parity (random-init end-to-end error alone cannot catch a broken attention kernel)."""
+    model, oracle = build_pair((1, 1, 1), "nearest+conv", 4, "stress", 21)
+    x = synthetic_image(1, 56, 72, seed=4)      # reflect padding for windows 16/32/48/64
+    taps = {}
+    with torch.no_grad():
+        oracle.forward(x, taps)
+    model = model.to(DEV)
+    xd = x.to(DEV)
+    names = ["shallow", "embed", "block0.0.qkv", "block0.0.scc", "block0.0.attn", "block0.0", "block0.1.scc", "block0.2.scc",
+             "block0.3.scc", "block0.4.scc", "block0.5.scc", "block0.5", "layer0", "layer5", "norm", "conv_after_body", "fused",
+             "conv_before_upsample", "up1", "up2", "hr"]
+    for n in names:
+        ref = taps[n].contiguous()
+        dst = torch.full((ref.numel(),), float("nan"), device=DEV)
+        model.set_tap(DEV, n, dst, stop=True)
+        with torch.no_grad():
+            model(xd)
+        torch.cuda.synchronize()
+        got = dst.cpu().view(ref.shape)
+        assert not torch.isnan(got).any(), n
+        assert rel_l2(got, ref) < TAP_REL_L2, (n, rel_l2(got, ref))
+    model.set_tap(DEV, None)
+
+
+@pytest.mark.parametrize("flags,up,scale,shape", [
+    ((1, 1, 1), "nearest+conv", 4, (2, 33, 33)),          # minimum size, batch 2
+    ((0, 0, 0), "nearest+conv", 4, (1, 64, 64)),          # cfg5 ablation path
+    ((1, 1, 1), "pixelshuffle", 4, (1, 40, 48)),
+    ((0, 1, 1), "pixelshuffledirect", 4, (1, 36, 52)),
+    ((1, 0, 0), "pixelshuffledirect", 2, (3, 35, 37)),
+])
+def test_cuda_matches_oracle_variants(flags, up, scale, shape):
+    model, oracle = build_pair(flags, up, scale, "stress", 31)
+    x = synthetic_image(*shape, seed=6)
+    with torch.no_grad():
+        ref = oracle(x)
+    y = run_cuda(model, x)
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() < TOL_MAXABS["stress"]
+    assert psnr(y, ref) > TOL_PSNR_DB["stress"]
+
+
+def test_batch_independence_and_determinism():
+    model, _ = build_pair((1, 1, 1), "nearest+conv", 4, "init", 41)
+    x = synthetic_image(3, 40, 44, seed=8)
+    y = run_cuda(model, x)
+    y2 = run_cuda(model, x)
+    assert torch.equal(y, y2)                               # bitwise reproducible (no float atomics on the path)
+    y_single = run_cuda(model, x[1:2])
+    assert (y[1:2] - y_single).abs().max().item() < 1e-5    # images of a batch are independent (reference: 6e-8)
+
+
+def test_psnr_equivalence_against_ground_truth():
+    """north_star: output PSNR against a ground truth within 0.01 dB of the reference's."""
+    model, oracle = build_pair((1, 1, 1), "nearest+conv", 4, "init", 51)
+    x = synthetic_image(1, 64, 64, seed=12)
+    gt = torch.nn.functional.interpolate(x, scale_factor=4, mode="bicubic", align_corners=False).clamp(0, 1)
+    with torch.no_grad():
+        ref = oracle(x)
+    y = run_cuda(model, x)
+    assert abs(psnr(y.clamp(0, 1), gt) - psnr(ref.clamp(0, 1), gt)) < 0.01
+
+
+def test_errors_mirror_reference():
+    model, _ = build_pair((0, 0, 0), "pixelshuffledirect", 2, "init", 3)
+    model = model.to(DEV)
+    with pytest.raises(RuntimeError):                       # hit_sir_pro.py:672: reflect pad needs pad < dim
+        model(torch.rand(1, 3, 32, 32, device=DEV))
+    with pytest.raises(RuntimeError):                       # no CPU path
+        model(torch.rand(1, 3, 64, 64))
+
+
+def test_state_dict_roundtrip_and_weight_update():
+    model, oracle = build_pair((0, 0, 0), "pixelshuffledirect", 2, "stress", 61)
+    x = synthetic_image(1, 40, 40, seed=2)
+    y1 = run_cuda(model, x)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    sd["conv_after_body.bias"] += 0.5
+    model.load_state_dict(sd)                               # in-place copy_ bumps _version -> re-pack
+    y2 = run_cuda(model, x)
+    assert (y1 - y2).abs().max().item() > 1e-3
+    from oracle.hitsir_oracle import HiTSIROracle
+    with torch.no_grad():
+        ref = HiTSIROracle({k: v.cpu() for k, v in sd.items()}, oracle.cfg)(x)
+    assert (y2 - ref).abs().max().item() < TOL_MAXABS["stress"]
+
+
+def test_forward_host_matches_forward():
+    model, _ = build_pair((1, 1, 1), "nearest+conv", 4, "init", 71)
+    x = synthetic_image(2, 48, 48, seed=9)
+    y = run_cuda(model, x)
+    yh = model.forward_host(x.pin_memory())
+    assert torch.equal(y, yh.clone())
