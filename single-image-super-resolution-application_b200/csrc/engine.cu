@@ -88,6 +88,7 @@ struct HitsirHandle {
   int device = 0;
   int num_sms = 148;
   bool simt = false;
+  bool direct_epilogue = false;   // HITSIR_EPILOGUE=direct: per-row global stores instead of the TMA-staged epilogue
   std::vector<ParamSpec> params;
   std::map<std::string, int> index;
   float* arena = nullptr;      // device fp32 master copy of every parameter
@@ -571,20 +572,37 @@ void base_params(GemmParams& p, const GemmW& w) {
   p.slope = 1.f;
 }
 
-int run_gemm(Fwd& f, const char* cat, const GemmW& w, GemmParams& p, const CUtensorMap& ta) {
+// The staged-epilogue kernel covers the plain-store and LayerNorm epilogues; the gate / pixel-shuffle
+// epilogues (once per forward) keep the direct-store kernel.
+bool tma_epilogue(const HitsirHandle* h, const GemmW& w, const GemmParams& p) {
+  return !h->simt && !h->direct_epilogue && (p.epi == EPI_STORE || p.epi == EPI_LN) && (w.BN == 192 || w.BN == 64) &&
+         p.out2_f32 == nullptr && w.Npad <= 384;
+}
+
+int run_gemm(Fwd& f, const char* cat, const GemmW& w, GemmParams& p, const CUtensorMap* maps, bool tma) {
   ProfScope ps(f.h, f.st, cat);
   f.h->launches++;
   if (f.h->simt) return launch_simt_gemm(w.BN, p, f.st);
-  return launch_umma_gemm(w.BN, p, ta, w.tm, f.h->num_sms, f.st);
+  if (tma) return launch_umma_gemm_tma(w.BN, p, maps, f.h->num_sms, f.st);
+  return launch_umma_gemm(w.BN, p, maps[0], w.tm, f.h->num_sms, f.st);
 }
 
 // token-major linear: A [M, lda] bf16 (lda == w.K)
 int linear(Fwd& f, const char* cat, const GemmW& w, const bf16* A, long long M, GemmParams& p) {
   p.conv = 0; p.M = (int)M; p.m_tiles = (int)cdiv64(M, 128);
   p.A = A; p.lda = w.K;
-  CUtensorMap ta;
-  if (!f.h->simt && make_tmap_2d(&ta, A, (uint64_t)w.K, (uint64_t)M, (uint64_t)w.K * 2, 64, 128)) return 1;
-  return run_gemm(f, cat, w, p, ta);
+  CUtensorMap maps[5];
+  const bool tma = tma_epilogue(f.h, w, p);
+  if (!f.h->simt) {
+    if (make_tmap_2d(&maps[0], A, (uint64_t)w.K, (uint64_t)M, (uint64_t)w.K * 2, 64, 128)) return 1;
+    maps[1] = w.tm; maps[2] = maps[0]; maps[3] = maps[0]; maps[4] = maps[0];
+    if (tma) {
+      if (p.out_f32 && make_tmap_2d_t(&maps[2], p.out_f32, 4, (uint64_t)p.n_real, (uint64_t)M, (uint64_t)p.ldf * 4, 32, 128)) return 1;
+      if (p.out_bf16 && make_tmap_2d_t(&maps[3], p.out_bf16, 2, (uint64_t)p.ldb, (uint64_t)M, (uint64_t)p.ldb * 2, 64, 128)) return 1;
+      if (p.res && make_tmap_2d_t(&maps[4], p.res, 4, (uint64_t)p.n_real, (uint64_t)M, (uint64_t)p.ldr * 4, 32, 128)) return 1;
+    }
+  }
+  return run_gemm(f, cat, w, p, maps, tma);
 }
 
 // 3x3 conv over NHWC bf16 [B,H,W,Cpad]
@@ -595,9 +613,18 @@ int conv3(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, 
   p.cblocks = Cpad / 64;
   p.A = A; p.lda = Cpad;
   if (w.K != 9 * Cpad) { set_error("conv3: packed K %d != 9*%d", w.K, Cpad); return 1; }
-  CUtensorMap ta;
-  if (!f.h->simt && make_tmap_nhwc(&ta, A, B, H, W, Cpad, 64, 16, 8)) return 1;
-  return run_gemm(f, cat, w, p, ta);
+  CUtensorMap maps[5];
+  const bool tma = tma_epilogue(f.h, w, p);
+  if (!f.h->simt) {
+    if (make_tmap_nhwc(&maps[0], A, B, H, W, Cpad, 64, 16, 8)) return 1;
+    maps[1] = w.tm; maps[2] = maps[0]; maps[3] = maps[0]; maps[4] = maps[0];
+    if (tma) {
+      if (p.out_f32 && make_tmap_nhwc_t(&maps[2], p.out_f32, 4, B, H, W, p.n_real, p.ldf, 32, 16, 8)) return 1;
+      if (p.out_bf16 && make_tmap_nhwc_t(&maps[3], p.out_bf16, 2, B, H, W, p.ldb, p.ldb, 64, 16, 8)) return 1;
+      if (p.res && make_tmap_nhwc_t(&maps[4], p.res, 4, B, H, W, p.n_real, p.ldr, 32, 16, 8)) return 1;
+    }
+  }
+  return run_gemm(f, cat, w, p, maps, tma);
 }
 
 #define TAP(name, src, is_bf16, ld, rows, cols) do { RUN(do_tap(f, name, src, is_bf16, ld, rows, cols)); if (f.stopped) return 0; } while (0)
@@ -825,6 +852,8 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
   if (cfg->in_chans == 3) { h->mean[0] = 0.485f; h->mean[1] = 0.456f; h->mean[2] = 0.4060f; }   // (:1128)
   const char* env = getenv("HITSIR_GEMM");
   h->simt = env && strcmp(env, "simt") == 0;
+  const char* env2 = getenv("HITSIR_EPILOGUE");
+  h->direct_epilogue = env2 && strcmp(env2, "direct") == 0;
   build_param_list(h);
   e = cudaMalloc(reinterpret_cast<void**>(&h->arena), h->arena_floats * sizeof(float));
   if (e != cudaSuccess) { set_error("cudaMalloc(param arena): %s", cudaGetErrorString(e)); delete h; return HITSIR_ERR_CUDA; }
@@ -939,7 +968,8 @@ HITSIR_API int hitsir_profile_get(HitsirHandle* h, int i, const char** name, dou
 
 HITSIR_API int hitsir_set_gemm_backend(HitsirHandle* h, const char* backend) {
   if (!h || !backend) { set_error("null argument"); return HITSIR_ERR_INVALID; }
-  if (strcmp(backend, "umma") == 0) h->simt = false;
+  if (strcmp(backend, "umma") == 0) { h->simt = false; h->direct_epilogue = false; }
+  else if (strcmp(backend, "umma_direct") == 0) { h->simt = false; h->direct_epilogue = true; }
   else if (strcmp(backend, "simt") == 0) h->simt = true;
   else { set_error("unknown gemm backend '%s' (umma|simt)", backend); return HITSIR_ERR_INVALID; }
   return 0;

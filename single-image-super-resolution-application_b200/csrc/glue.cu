@@ -67,45 +67,91 @@ __global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restr
   }
 }
 
-// thread = (pixel, 8 channels); h2 = h1 + gelu(dw5x5(h1) + b)
-__global__ void dwconv5_kernel(const bf16* __restrict__ h1, const float* __restrict__ wt, const float* __restrict__ bias, bf16* __restrict__ h2,
-                               int B, int H, int W) {
-  constexpr int groups = kHidp / 8;   // 48
-  const long long total = (long long)B * H * W * groups;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int gidx = (int)(idx % groups);
-    const long long pix = idx / groups;
-    const int xw = (int)(pix % W); const long long t = pix / W; const int y = (int)(t % H); const int b = (int)(t / H);
-    const int c0 = gidx * 8;
-    float acc[8];
+// h2 = h1 + gelu(dw5x5(h1) + b)   (ConvFFN middle, hit_sir_pro.py:42 with :15-17).
+// CTA = 8 x 32 pixel tile x 64 channels.  The (8+4) x (32+4) x 64 bf16 input patch is staged once in shared
+// memory (zero halo = the conv's zero padding); thread = (row, 4 consecutive x, 8 channels) x 2 passes: 8 input
+// vectors per filter row feed 4 outputs, filter taps are re-read from smem once per filter row; packed fp32 FMA.
+constexpr int kDwTH = 8, kDwTW = 32, kDwCC = 64;
+constexpr int kDwPW = kDwTW + 4, kDwPH = kDwTH + 4;
+
+__global__ void __launch_bounds__(256, 2) dwconv5_tiled_kernel(const bf16* __restrict__ h1, const float* __restrict__ wt, const float* __restrict__ bias,
+                                                            bf16* __restrict__ h2, int B, int H, int W, int tiles_x, int tiles_y) {
+  extern __shared__ __align__(16) uint8_t dw_smem[];
+  uint4* tile = reinterpret_cast<uint4*>(dw_smem);                       // [kDwPH*kDwPW][8] x 16 B
+  float* w_s = reinterpret_cast<float*>(dw_smem + kDwPH * kDwPW * 128);   // [25][64]
+  float* b_s = w_s + 25 * kDwCC;                                          // [64]
+  const int cchunk = blockIdx.y;                       // 64-channel slice
+  const int tx = blockIdx.x % tiles_x; const int t2 = blockIdx.x / tiles_x;
+  const int ty = t2 % tiles_y; const int b = t2 / tiles_y;
+  const int y0 = ty * kDwTH, x0 = tx * kDwTW;
+  const int cbase = cchunk * kDwCC;
+  for (int i = threadIdx.x; i < 25 * kDwCC; i += 256) w_s[i] = wt[(i / kDwCC) * kHidp + cbase + (i % kDwCC)];
+  if (threadIdx.x < kDwCC) b_s[threadIdx.x] = bias[cbase + threadIdx.x];
+  for (int i = threadIdx.x; i < kDwPH * kDwPW * 8; i += 256) {
+    const int ch = i & 7, pp = i >> 3;
+    const int py = pp / kDwPW, px = pp - py * kDwPW;
+    const int yy = y0 + py - 2, xx = x0 + px - 2;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
+      v = __ldg(reinterpret_cast<const uint4*>(h1 + (((long long)b * H + yy) * W + xx) * kHidp + cbase) + ch);
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int grp = threadIdx.x & 7;                     // 8-channel group inside the 64-channel slice
+  const int row = threadIdx.x >> 5;                    // tile row
+  const int y = y0 + row;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {
+    const int xq = ((threadIdx.x >> 3) & 3) + 4 * pass;  // which run of 4 pixels along x (8 runs per tile row)
+    float2 acc[4][4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = __ldg(bias + c0 + e);
-    float center[8];
+    for (int o = 0; o < 4; ++o)
 #pragma unroll
+      for (int j = 0; j < 4; ++j) acc[o][j] = make_float2(b_s[grp * 8 + 2 * j], b_s[grp * 8 + 2 * j + 1]);
+#pragma unroll 1
     for (int ky = 0; ky < 5; ++ky) {
-      const int yy = y + ky - 2;
-      if (yy < 0 || yy >= H) continue;
+      float2 wr[5][4];
 #pragma unroll
       for (int kx = 0; kx < 5; ++kx) {
-        const int xx = xw + kx - 2;
-        if (xx < 0 || xx >= W) continue;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(h1 + (((long long)b * H + yy) * W + xx) * kHidp + c0));
-        const float4 w0 = __ldg(reinterpret_cast<const float4*>(wt + (ky * 5 + kx) * kHidp + c0));
-        const float4 w1 = __ldg(reinterpret_cast<const float4*>(wt + (ky * 5 + kx) * kHidp + c0 + 4));
-        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-        acc[0] += f0.x * w0.x; acc[1] += f0.y * w0.y; acc[2] += f1.x * w0.z; acc[3] += f1.y * w0.w;
-        acc[4] += f2.x * w1.x; acc[5] += f2.y * w1.y; acc[6] += f3.x * w1.z; acc[7] += f3.y * w1.w;
-        if (ky == 2 && kx == 2) {
-          center[0] = f0.x; center[1] = f0.y; center[2] = f1.x; center[3] = f1.y;
-          center[4] = f2.x; center[5] = f2.y; center[6] = f3.x; center[7] = f3.y;
+        const float4 a = *reinterpret_cast<const float4*>(w_s + (ky * 5 + kx) * kDwCC + grp * 8);
+        const float4 c = *reinterpret_cast<const float4*>(w_s + (ky * 5 + kx) * kDwCC + grp * 8 + 4);
+        wr[kx][0] = make_float2(a.x, a.y); wr[kx][1] = make_float2(a.z, a.w);
+        wr[kx][2] = make_float2(c.x, c.y); wr[kx][3] = make_float2(c.z, c.w);
+      }
+#pragma unroll
+      for (int xi = 0; xi < 8; ++xi) {
+        const uint4 u = tile[((row + ky) * kDwPW + xq * 4 + xi) * 8 + grp];
+        const float2 v[4] = {unpack_bf16x2(u.x), unpack_bf16x2(u.y), unpack_bf16x2(u.z), unpack_bf16x2(u.w)};
+#pragma unroll
+        for (int o = 0; o < 4; ++o) {
+          const int kx = xi - o;                       // compile-time after unrolling
+          if (kx >= 0 && kx < 5) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[o][j] = __ffma2_rn(v[j], wr[kx][j], acc[o][j]);
+          }
         }
       }
     }
-    float o[8];
+    if (y < H) {
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = (c0 + e < kHid) ? center[e] + gelu_erf(acc[e]) : 0.f;
-    *reinterpret_cast<uint4*>(h2 + pix * kHidp + c0) =
-        make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+      for (int o = 0; o < 4; ++o) {
+        const int x = x0 + xq * 4 + o;
+        if (x >= W) continue;
+        const uint4 u = tile[((row + 2) * kDwPW + xq * 4 + o + 2) * 8 + grp];       // the un-convolved input (residual term)
+        const float2 cv[4] = {unpack_bf16x2(u.x), unpack_bf16x2(u.y), unpack_bf16x2(u.z), unpack_bf16x2(u.w)};
+        float r[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          r[2 * j] = cv[j].x + gelu_fast(acc[o][j].x);
+          r[2 * j + 1] = cv[j].y + gelu_fast(acc[o][j].y);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (cbase + grp * 8 + e >= kHid) r[e] = 0.f;
+        *reinterpret_cast<uint4*>(h2 + (((long long)b * H + y) * W + x) * kHidp + cbase + grp * 8) =
+            make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
+      }
+    }
   }
 }
 
@@ -260,6 +306,67 @@ __global__ void qkv_build_kernel(const float* __restrict__ x, PadGeom g, int cas
   }
 }
 
+// casa gate, fast path: CTA = (image b, padded row yp, run of 64 padded pixels); thread = channel pair.
+// The two 3x3 filters of a channel pair live in registers, the 3 x 66 window of both statistic maps in shared
+// memory; per pixel a thread does 18 packed FMAs, one 8-byte token load and one 4-byte bf16x2 store, so a warp
+// reads/writes whole contiguous token rows.
+constexpr int kQkvRun = 64;
+__global__ void __launch_bounds__(96) qkv_casa_kernel(const float* __restrict__ x, PadGeom g, const float* __restrict__ cavg,
+                                                      const float* __restrict__ cmax, const float* __restrict__ s1, const float* __restrict__ s2,
+                                                      CasaW w, bf16* __restrict__ t, int runs) {
+  __shared__ float sa[3][kQkvRun + 2], sm[3][kQkvRun + 2];
+  const int run = blockIdx.x % runs; const int t2 = blockIdx.x / runs;
+  const int yp = t2 % g.Hp; const int b = t2 / g.Hp;
+  const int xs = run * kQkvRun;
+  const float* ca = cavg + (long long)b * g.Hp * g.Wp;
+  const float* cm = cmax + (long long)b * g.Hp * g.Wp;
+  for (int i = threadIdx.x; i < 3 * (kQkvRun + 2); i += 96) {
+    const int rr = i / (kQkvRun + 2), cc = i - rr * (kQkvRun + 2);
+    const int yy = yp + rr - 1, xx = xs + cc - 1;
+    const bool ok = yy >= 0 && yy < g.Hp && xx >= 0 && xx < g.Wp;     // zero padding of the PADDED map
+    sa[rr][cc] = ok ? ca[yy * g.Wp + xx] : 0.f;
+    sm[rr][cc] = ok ? cm[yy * g.Wp + xx] : 0.f;
+  }
+  const int c = 2 * threadIdx.x;
+  const bool live = c < kC;
+  float2 w1[9], w2[9], b1 = make_float2(0.f, 0.f), b2 = b1, g1 = b1, g2 = b1;
+  if (live) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      w1[tap] = *reinterpret_cast<const float2*>(w.w1 + tap * kC + c);
+      w2[tap] = *reinterpret_cast<const float2*>(w.w2 + tap * kC + c);
+    }
+    b1 = *reinterpret_cast<const float2*>(w.b1 + c); b2 = *reinterpret_cast<const float2*>(w.b2 + c);
+    g1 = *reinterpret_cast<const float2*>(s1 + (long long)b * kC + c); g2 = *reinterpret_cast<const float2*>(s2 + (long long)b * kC + c);
+  } else {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) { w1[tap] = make_float2(0.f, 0.f); w2[tap] = w1[tap]; }
+  }
+  __syncthreads();
+  const int ysrc = reflect_src(yp, g.H);
+  const int n = min(kQkvRun, g.Wp - xs);
+  for (int i = 0; i < n; ++i) {
+    const int xp = xs + i;
+    uint32_t packed = 0u;
+    if (live) {
+      const float2 xv = *reinterpret_cast<const float2*>(x + (((long long)b * g.H + ysrc) * g.W + reflect_src(xp, g.W)) * kC + c);
+      float2 a1 = b1, a2 = b2;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const float va = sa[ky][i + kx], vm = sm[ky][i + kx];
+          a1 = __ffma2_rn(w1[ky * 3 + kx], make_float2(va, va), a1);
+          a2 = __ffma2_rn(w2[ky * 3 + kx], make_float2(vm, vm), a2);
+        }
+      const float o0 = xv.x + 0.5f * (lrelu(a1.x, 0.2f) * g1.x + lrelu(a2.x, 0.2f) * g2.x);     // (:345-359)
+      const float o1 = xv.y + 0.5f * (lrelu(a1.y, 0.2f) * g1.y + lrelu(a2.y, 0.2f) * g2.y);
+      packed = pack_bf16x2(o0, o1);
+    }
+    *reinterpret_cast<uint32_t*>(t + (((long long)b * g.Hp + yp) * g.Wp + xp) * kCp + c) = packed;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // UnionAttention statistics.  X = a (+ b).
 //   rows kernel : CTA per (b, y): channel mean/max per pixel + mean/max over W per channel.
@@ -397,8 +504,15 @@ int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* 
   return 0;
 }
 int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, bf16* h2, int B, int H, int W, cudaStream_t st) {
-  const long long total = (long long)B * H * W * (kHidp / 8);
-  dwconv5_kernel<<<grid_for(total, 192), 192, 0, st>>>(h1, w, bias, h2, B, H, W);
+  static bool configured = false;
+  const int smem = kDwPH * kDwPW * 128 + 25 * kDwCC * 4 + kDwCC * 4;
+  if (!configured) {
+    HITSIR_CHECK(cudaFuncSetAttribute(dwconv5_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int tiles_x = (W + kDwTW - 1) / kDwTW, tiles_y = (H + kDwTH - 1) / kDwTH;
+  dim3 grid(tiles_x * tiles_y * B, kHidp / kDwCC);
+  dwconv5_tiled_kernel<<<grid, 256, smem, st>>>(h1, w, bias, h2, B, H, W, tiles_x, tiles_y);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
@@ -436,6 +550,12 @@ int launch_sca_mlp(const float* part_sum, const float* part_max, int nparts, Pad
 }
 int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, const float* cmax, const float* s1, const float* s2, CasaW w, bf16* t,
                      cudaStream_t st) {
+  if (casa) {
+    const int runs = (g.Wp + kQkvRun - 1) / kQkvRun;
+    qkv_casa_kernel<<<g.B * g.Hp * runs, 96, 0, st>>>(x, g, cavg, cmax, s1, s2, w, t, runs);
+    HITSIR_CHECK(cudaGetLastError());
+    return 0;
+  }
   const long long total = (long long)g.B * g.Hp * g.Wp * (kCp / 8);
   qkv_build_kernel<<<grid_for(total, 192), 192, 0, st>>>(x, g, casa, cavg, cmax, s1, s2, w, t);
   HITSIR_CHECK(cudaGetLastError());

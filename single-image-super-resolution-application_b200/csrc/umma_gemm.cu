@@ -177,13 +177,19 @@ static PFN_encodeTiled get_encode() {
 
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                  uint32_t box_inner, uint32_t box_outer) {
+  return make_tmap_2d_t(m, base, 2, inner, outer, pitch_bytes, box_inner, box_outer);
+}
+
+int make_tmap_2d_t(CUtensorMap* m, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                   uint32_t box_inner, uint32_t box_outer) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return 1;
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {pitch_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -195,13 +201,22 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t oute
 }
 
 int make_tmap_nhwc(CUtensorMap* m, const void* base, int B, int H, int W, int Cpad, uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+  return make_tmap_nhwc_t(m, base, 2, B, H, W, Cpad, Cpad, box_c, box_w, box_h);
+}
+
+// NHWC tensor with `C` visible channels out of a pixel pitch of `ldc` elements
+int make_tmap_nhwc_t(CUtensorMap* m, const void* base, int elem_bytes, int B, int H, int W, int C, int ldc, uint32_t box_c, uint32_t box_w,
+                     uint32_t box_h) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) return 1;
-  cuuint64_t dims[4] = {(cuuint64_t)Cpad, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)Cpad * 2, (cuuint64_t)W * Cpad * 2, (cuuint64_t)H * W * Cpad * 2};
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const int Cpad = C;
+  const cuuint64_t eb = (cuuint64_t)elem_bytes;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ldc * eb, (cuuint64_t)W * ldc * eb, (cuuint64_t)H * W * ldc * eb};
   cuuint32_t box[4] = {box_c, box_w, box_h, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+  CUresult r = enc(m, dt, 4, const_cast<void*>(base), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
