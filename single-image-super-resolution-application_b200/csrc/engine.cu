@@ -45,6 +45,7 @@ struct BlockW {
   float *casa_w1 = nullptr, *casa_w2 = nullptr;
   SccW scc;
   float* bias_tbl = nullptr;
+  uint8_t *pool_img = nullptr, *bias_img = nullptr, *w_img = nullptr;
   GemmW proj, fc1, fc2;
   float *dw_w = nullptr, *dw_b = nullptr;
 };
@@ -238,7 +239,7 @@ int validate_config(const HitsirConfig& c) {
       if (w < 1) { set_error("window %d of block %d is empty", w, j); return HITSIR_ERR_INVALID; }
       // reference assertion, hit_sir_pro.py:647-649
       if (w > bs && w % bs != 0) { set_error("please ensure the window size is smaller than or divisible by the base window size"); return HITSIR_ERR_INVALID; }
-      if (w > 64) { set_error("window %d > 64 not supported by this build", w); return HITSIR_ERR_UNSUPPORTED; }
+      if (scc_tile(w).TT == 0) { set_error("window %d not supported by this build (4, 8, 16, 32, 48, 64)", w); return HITSIR_ERR_UNSUPPORTED; }
     }
   }
   if (c.upsampler == HITSIR_UP_NEAREST_CONV && c.upscale != 4) { set_error("only support x4 now."); return HITSIR_ERR_INVALID; }   // (:1248)
@@ -278,7 +279,7 @@ int pick_bn(int n) {
 }
 
 // conv (taps=9) or linear (taps=1) weight `prefix` -> packed GEMM operand
-int make_gemm_w(HitsirHandle* h, GemmW* g, const std::string& prefix, int Co, int Ci, int taps, cudaStream_t st) {
+int make_gemm_w(HitsirHandle* h, GemmW* g, const std::string& prefix, int Co, int Ci, int taps, cudaStream_t st, int perm_k = 0) {
   const int BN = pick_bn(Co);
   const int Npad = round_up(Co, BN), Cipad = round_up(Ci, 64);
   g->BN = BN; g->Npad = Npad; g->K = taps * Cipad;
@@ -287,7 +288,7 @@ int make_gemm_w(HitsirHandle* h, GemmW* g, const std::string& prefix, int Co, in
   const float* w = P(h, prefix + ".weight");
   const float* b = P(h, prefix + ".bias");
   if (!w || !b) { set_error("missing parameter %s", prefix.c_str()); return 1; }
-  if (launch_pack_conv(w, b, g->w, g->b, Co, Ci, taps, Npad, Cipad, st)) return 1;
+  if (launch_pack_conv(w, b, g->w, g->b, Co, Ci, taps, Npad, Cipad, perm_k, st)) return 1;
   return make_tmap_2d(&g->tm, g->w, (uint64_t)g->K, (uint64_t)Npad, (uint64_t)g->K * 2, 64, (uint32_t)BN);
 }
 
@@ -367,7 +368,12 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
       if (launch_pos_table(pw, bw.win, tbl_scratch, st)) return 1;
       if (launch_pooled_bias(tbl_scratch, bw.win, bw.base, bw.bias_tbl, st)) return 1;
       bw.scc.bias_tbl = bw.bias_tbl;
-      if (make_gemm_w(h, &bw.proj, s + ".proj", C, C, 1, st)) return 1;
+      if (dev_alloc(h, &bw.pool_img, scc_pool_image_bytes(bw.win)) || dev_alloc(h, &bw.bias_img, scc_bias_image_bytes(bw.win)) ||
+          dev_alloc(h, &bw.w_img, 2048)) return 1;
+      if (launch_scc_images(bw.scc, bw.win, bw.base, bw.pool_img, bw.bias_img, bw.w_img, st)) return 1;
+      bw.scc.pool_img = bw.pool_img; bw.scc.bias_img = bw.bias_img; bw.scc.w_img = bw.w_img;
+      // proj consumes the SCC output in its head-padded channel order (kernels.cuh scc_pos)
+      if (make_gemm_w(h, &bw.proj, s + ".proj", C, C, 1, st, 1)) return 1;
       if (make_gemm_w(h, &bw.fc1, p + ".mlp.fc1", kHid, C, 1, st)) return 1;
       if (make_gemm_w(h, &bw.fc2, p + ".mlp.fc2", C, kHid, 1, st)) return 1;
       if (dev_alloc(h, &bw.dw_w, 25 * kHidp) || dev_alloc(h, &bw.dw_b, kHidp)) return 1;
@@ -433,7 +439,7 @@ struct Workspace {
   bf16* T = nullptr;                                     // bf16 [NpMax,192] qkv tokens on the padded map
   float *cavg = nullptr, *cmax = nullptr;                // [NpMax]
   float *part_sum = nullptr, *part_max = nullptr, *s1 = nullptr, *s2 = nullptr;
-  float *scc_part = nullptr, *scc_fin = nullptr;
+  float* scc_dbg = nullptr;
   bf16* outsc = nullptr;                                 // bf16 [N,192]
   bf16 *H1 = nullptr, *H2 = nullptr;                     // bf16 [N,384] (contiguous: also G [N,768], A1|A2 fp32)
   float *havg, *hmax, *wavg, *wmax, *c_att, *h_att, *w_att;
@@ -452,18 +458,10 @@ struct Bump {
   }
 };
 
-int scc_parts(int L) {
-  if (L <= 256) return 1;
-  for (int p = 2; p <= L; ++p)
-    if (L % p == 0 && L / p <= 256) return p;
-  return L;
-}
-
 int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Workspace* ws) {
   const HitsirConfig& c = h->cfg;
   const size_t N = (size_t)B * H * W;
   size_t np_max = N;
-  long long part_max_f = 0, fin_max_f = 0;
   int max_depth = 0;
   for (int i = 0; i < c.num_layers; ++i) max_depth = c.depths[i] > max_depth ? c.depths[i] : max_depth;
   for (int j = 0; j < max_depth; ++j) {
@@ -476,14 +474,6 @@ int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Wor
     }
     const size_t np = (size_t)B * Hp * Wp;
     np_max = np > np_max ? np : np_max;
-    SccGeom g;
-    g.pg = PadGeom{B, H, W, Hp, Wp};
-    g.w = w; g.base = w < c.base_win_size[0] ? w : c.base_win_size[0]; g.r = w / g.base;
-    g.L = w * w; g.Lb = g.base * g.base; g.nWy = Hp / w; g.nWx = Wp / w; g.parts = scc_parts(g.L);
-    long long pf, ff;
-    scc_workspace_floats(g, &pf, &ff);
-    part_max_f = pf > part_max_f ? pf : part_max_f;
-    fin_max_f = ff > fin_max_f ? ff : fin_max_f;
   }
   Bump b{reinterpret_cast<uint8_t*>(base)};
   ws->P = b.take<float>(N * kC);
@@ -499,8 +489,7 @@ int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Wor
   ws->part_max = b.take<float>((size_t)B * ws->nparts * kC);
   ws->s1 = b.take<float>((size_t)B * kC);
   ws->s2 = b.take<float>((size_t)B * kC);
-  ws->scc_part = b.take<float>((size_t)part_max_f);
-  ws->scc_fin = b.take<float>((size_t)fin_max_f);
+  ws->scc_dbg = b.take<float>((size_t)kSccDbgFloats);
   ws->outsc = b.take<bf16>(N * kCp);
   ws->H1 = b.take<bf16>(N * kHidp * 2);  // H1 | H2 contiguous
   ws->H2 = ws->H1 ? ws->H1 + N * kHidp : nullptr;
@@ -538,11 +527,11 @@ struct Fwd {
 };
 
 // returns 1 on error, sets f.stopped when the requested tap asked to stop
-int do_tap(Fwd& f, const char* name, const void* src, int is_bf16, int ld, long long rows, int cols) {
+int do_tap(Fwd& f, const char* name, const void* src, int is_bf16, int ld, long long rows, int cols, int perm = 0) {
   Tap& t = f.h->tap;
   if (t.dst == nullptr || t.name != name) return 0;
   if (rows * cols > t.floats) { set_error("tap '%s' needs %lld floats, destination has %lld", name, rows * cols, (long long)t.floats); return HITSIR_ERR_INVALID; }
-  if (launch_f32_to_f32_tap(src, is_bf16, ld, t.dst, rows, cols, f.st)) return 1;
+  if (launch_f32_to_f32_tap(src, is_bf16, ld, t.dst, rows, cols, perm, f.st)) return 1;
   if (t.stop) f.stopped = true;
   return 0;
 }
@@ -628,6 +617,7 @@ int conv3(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, 
 }
 
 #define TAP(name, src, is_bf16, ld, rows, cols) do { RUN(do_tap(f, name, src, is_bf16, ld, rows, cols)); if (f.stopped) return 0; } while (0)
+#define TAPP(name, src, is_bf16, ld, rows, cols) do { RUN(do_tap(f, name, src, is_bf16, ld, rows, cols, 1)); if (f.stopped) return 0; } while (0)
 
 int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   // HierarchicalTransformerBlock.forward (:676-706); xin -> xout after the attention half, then in place on xout
@@ -640,16 +630,21 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   SccGeom g;
   g.pg = PadGeom{f.B, f.H, f.W, round_up(f.H, w), round_up(f.W, w)};
   g.w = w; g.base = bw.base; g.r = bw.r; g.L = w * w; g.Lb = bw.base * bw.base;
-  g.nWy = g.pg.Hp / w; g.nWx = g.pg.Wp / w; g.parts = scc_parts(g.L);
+  g.nWy = g.pg.Hp / w; g.nWx = g.pg.Wp / w; g.parts = 1;
   const long long Np = (long long)f.B * g.pg.Hp * g.pg.Wp;
   if (c.is_channel_spatial_attn) {
     LAUNCH("sca_stats", 1, launch_sca_stats(xin, g.pg, ws.cavg, ws.cmax, ws.part_sum, ws.part_max, ws.nparts, f.st));
     LAUNCH("sca_mlp", 1, launch_sca_mlp(ws.part_sum, ws.part_max, ws.nparts, g.pg, bw.casa, ws.s1, ws.s2, f.st));
   }
   LAUNCH("qkv_build", 1, launch_qkv_build(xin, g.pg, c.is_channel_spatial_attn, ws.cavg, ws.cmax, ws.s1, ws.s2, bw.casa, ws.T, f.st));
-  TAP((tn + ".qkv").c_str(), ws.T, 1, kCp, Np, kC);
-  { char cat[16]; snprintf(cat, sizeof(cat), "scc_w%d", w); LAUNCH(cat, (g.parts > 1 ? 3 : 1), launch_scc(ws.T, g, bw.scc, ws.scc_part, ws.scc_fin, ws.outsc, f.st)); }
-  TAP((tn + ".scc").c_str(), ws.outsc, 1, kCp, f.N, kC);
+  TAPP((tn + ".qkv").c_str(), ws.T, 1, kCp, Np, kC);
+  {
+    const bool want_dbg = h->tap.dst != nullptr && h->tap.name == tn + ".sccdbg";
+    char cat[16]; snprintf(cat, sizeof(cat), "scc_w%d", w);
+    LAUNCH(cat, 1, launch_scc_umma(ws.T, g, bw.scc, ws.outsc, want_dbg ? ws.scc_dbg : nullptr, h->num_sms, f.st));
+  }
+  TAP((tn + ".sccdbg").c_str(), ws.scc_dbg, 0, kSccDbgFloats, 1, kSccDbgFloats);
+  TAPP((tn + ".scc").c_str(), ws.outsc, 1, kCp, f.N, kC);
   GemmParams p;
   // proj + norm1 + residual (:597, :700-703)
   base_params(p, bw.proj);

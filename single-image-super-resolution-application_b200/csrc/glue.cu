@@ -173,10 +173,11 @@ __global__ void fill_kernel(float* p, float v, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
 
-__global__ void tap_kernel(const void* src, int is_bf16, int ld, float* dst, long long rows, int cols) {
+__global__ void tap_kernel(const void* src, int is_bf16, int ld, float* dst, long long rows, int cols, int perm) {
   const long long total = rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cols; const int c = (int)(i - r * cols);
+    const long long r = i / cols; const int c0 = (int)(i - r * cols);
+    const int c = perm ? scc_pos(c0) : c0;
     dst[i] = is_bf16 ? __bfloat162float(reinterpret_cast<const bf16*>(src)[r * ld + c]) : reinterpret_cast<const float*>(src)[r * ld + c];
   }
 }
@@ -254,59 +255,28 @@ __global__ void __launch_bounds__(192) sca_mlp_kernel(const float* __restrict__ 
   }
 }
 
-// thread = (padded pixel, 8 channels)
-__global__ void qkv_build_kernel(const float* __restrict__ x, PadGeom g, int casa, const float* __restrict__ cavg, const float* __restrict__ cmax,
-                                 const float* __restrict__ s1, const float* __restrict__ s2, CasaW w, bf16* __restrict__ t) {
+// thread = (padded pixel, 8 head-padded positions); no casa gate (Identity qkv, :552)
+__global__ void qkv_build_kernel(const float* __restrict__ x, PadGeom g, bf16* __restrict__ t) {
   constexpr int groups = kCp / 8;   // 24
   const long long total = (long long)g.B * g.Hp * g.Wp * groups;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int gi = (int)(idx % groups);
     const long long pix = idx / groups;
     const int xp = (int)(pix % g.Wp); const long long tt = pix / g.Wp; const int yp = (int)(tt % g.Hp); const int b = (int)(tt / g.Hp);
-    const int c0 = gi * 8;
+    const float* r = x + (((long long)b * g.H + reflect_src(yp, g.H)) * g.W + reflect_src(xp, g.W)) * kC;
     float o[8];
-    if (c0 >= kC) {
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = 0.f;
-    } else {
-      const float* r = x + (((long long)b * g.H + reflect_src(yp, g.H)) * g.W + reflect_src(xp, g.W)) * kC + c0;
-      // rows are 720 B (16-byte aligned), c0 multiple of 8 -> two float4 loads; the tail group (c0=176) has only 4 channels
-      const float4 v0 = *reinterpret_cast<const float4*>(r);
-      float4 v1 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c0 + 4 < kC) v1 = *reinterpret_cast<const float4*>(r + 4);
-      o[0] = v0.x; o[1] = v0.y; o[2] = v0.z; o[3] = v0.w; o[4] = v1.x; o[5] = v1.y; o[6] = v1.z; o[7] = v1.w;
-      if (casa) {
-        float a1[8], a2[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { const int c = min(c0 + e, kC - 1); a1[e] = w.b1[c]; a2[e] = w.b2[c]; }
-        const float* ca = cavg + (long long)b * g.Hp * g.Wp;
-        const float* cm = cmax + (long long)b * g.Hp * g.Wp;
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-          const int yy = yp + tap / 3 - 1, xx = xp + tap % 3 - 1;
-          if (yy < 0 || yy >= g.Hp || xx < 0 || xx >= g.Wp) continue;    // zero padding of the PADDED map
-          const float va = ca[yy * g.Wp + xx], vm = cm[yy * g.Wp + xx];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = min(c0 + e, kC - 1);
-            a1[e] += w.w1[tap * kC + c] * va;
-            a2[e] += w.w2[tap * kC + c] * vm;
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = c0 + e;
-          if (c < kC) o[e] += 0.5f * (lrelu(a1[e], 0.2f) * s1[(long long)b * kC + c] + lrelu(a2[e], 0.2f) * s2[(long long)b * kC + c]);
-          else o[e] = 0.f;
-        }
-      }
+    for (int e = 0; e < 8; ++e) {
+      const int pos = gi * 8 + e, c = scc_chan(pos);
+      o[e] = c >= 0 ? r[c] : (pos == 15 ? 1.0f : 0.f);
     }
-    *reinterpret_cast<uint4*>(t + pix * kCp + c0) =
+    *reinterpret_cast<uint4*>(t + pix * kCp + gi * 8) =
         make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
   }
 }
 
-// casa gate, fast path: CTA = (image b, padded row yp, run of 64 padded pixels); thread = channel pair.
+// casa gate: CTA = (image b, padded row yp, run of 64 padded pixels); thread = pair of head-padded positions (2t, 2t+1);
+// an even position is never a pad, the odd one is a pad when (2t+1) % 16 == 15 (position 15 carries the constant 1).
 // The two 3x3 filters of a channel pair live in registers, the 3 x 66 window of both statistic maps in shared
 // memory; per pixel a thread does 18 packed FMAs, one 8-byte token load and one 4-byte bf16x2 store, so a warp
 // reads/writes whole contiguous token rows.
@@ -327,29 +297,28 @@ __global__ void __launch_bounds__(96) qkv_casa_kernel(const float* __restrict__ 
     sa[rr][cc] = ok ? ca[yy * g.Wp + xx] : 0.f;
     sm[rr][cc] = ok ? cm[yy * g.Wp + xx] : 0.f;
   }
-  const int c = 2 * threadIdx.x;
-  const bool live = c < kC;
-  float2 w1[9], w2[9], b1 = make_float2(0.f, 0.f), b2 = b1, g1 = b1, g2 = b1;
-  if (live) {
+  const int pos = 2 * threadIdx.x;
+  const int cA = scc_chan(pos), cb = scc_chan(pos + 1);
+  const int cbs = cb >= 0 ? cb : cA;                    // pad slot: compute a harmless duplicate, overwrite below
+  const float padv = (pos + 1 == 15) ? 1.0f : 0.f;
+  float2 w1[9], w2[9];
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      w1[tap] = *reinterpret_cast<const float2*>(w.w1 + tap * kC + c);
-      w2[tap] = *reinterpret_cast<const float2*>(w.w2 + tap * kC + c);
-    }
-    b1 = *reinterpret_cast<const float2*>(w.b1 + c); b2 = *reinterpret_cast<const float2*>(w.b2 + c);
-    g1 = *reinterpret_cast<const float2*>(s1 + (long long)b * kC + c); g2 = *reinterpret_cast<const float2*>(s2 + (long long)b * kC + c);
-  } else {
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) { w1[tap] = make_float2(0.f, 0.f); w2[tap] = w1[tap]; }
+  for (int tap = 0; tap < 9; ++tap) {
+    w1[tap] = make_float2(w.w1[tap * kC + cA], w.w1[tap * kC + cbs]);
+    w2[tap] = make_float2(w.w2[tap * kC + cA], w.w2[tap * kC + cbs]);
   }
+  const float2 b1 = make_float2(w.b1[cA], w.b1[cbs]), b2 = make_float2(w.b2[cA], w.b2[cbs]);
+  const float2 g1 = make_float2(s1[(long long)b * kC + cA], s1[(long long)b * kC + cbs]);
+  const float2 g2 = make_float2(s2[(long long)b * kC + cA], s2[(long long)b * kC + cbs]);
   __syncthreads();
   const int ysrc = reflect_src(yp, g.H);
   const int n = min(kQkvRun, g.Wp - xs);
   for (int i = 0; i < n; ++i) {
     const int xp = xs + i;
     uint32_t packed = 0u;
-    if (live) {
-      const float2 xv = *reinterpret_cast<const float2*>(x + (((long long)b * g.H + ysrc) * g.W + reflect_src(xp, g.W)) * kC + c);
+    {
+      const float* xr = x + (((long long)b * g.H + ysrc) * g.W + reflect_src(xp, g.W)) * kC;
+      const float2 xv = make_float2(xr[cA], xr[cbs]);
       float2 a1 = b1, a2 = b2;
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky)
@@ -361,9 +330,9 @@ __global__ void __launch_bounds__(96) qkv_casa_kernel(const float* __restrict__ 
         }
       const float o0 = xv.x + 0.5f * (lrelu(a1.x, 0.2f) * g1.x + lrelu(a2.x, 0.2f) * g2.x);     // (:345-359)
       const float o1 = xv.y + 0.5f * (lrelu(a1.y, 0.2f) * g1.y + lrelu(a2.y, 0.2f) * g2.y);
-      packed = pack_bf16x2(o0, o1);
+      packed = pack_bf16x2(o0, cb >= 0 ? o1 : padv);
     }
-    *reinterpret_cast<uint32_t*>(t + (((long long)b * g.Hp + yp) * g.Wp + xp) * kCp + c) = packed;
+    *reinterpret_cast<uint32_t*>(t + (((long long)b * g.Hp + yp) * g.Wp + xp) * kCp + pos) = packed;
   }
 }
 
@@ -527,8 +496,8 @@ int launch_fill_f32(float* p, float v, long long n, cudaStream_t st) {
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
-int launch_f32_to_f32_tap(const void* src, int is_bf16, int ld, float* dst, long long rows, int cols, cudaStream_t st) {
-  tap_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(src, is_bf16, ld, dst, rows, cols);
+int launch_f32_to_f32_tap(const void* src, int is_bf16, int ld, float* dst, long long rows, int cols, int perm, cudaStream_t st) {
+  tap_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(src, is_bf16, ld, dst, rows, cols, perm);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
@@ -557,7 +526,7 @@ int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, con
     return 0;
   }
   const long long total = (long long)g.B * g.Hp * g.Wp * (kCp / 8);
-  qkv_build_kernel<<<grid_for(total, 192), 192, 0, st>>>(x, g, casa, cavg, cmax, s1, s2, w, t);
+  qkv_build_kernel<<<grid_for(total, 192), 192, 0, st>>>(x, g, t);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

@@ -23,7 +23,8 @@ int launch_dwconv5_gelu_add(const bf16* h1, const float* w_tap_major, const floa
 // nearest x2 upsample of an NHWC bf16 map with C channels
 int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st);
 int launch_fill_f32(float* p, float v, long long n, cudaStream_t st);
-int launch_f32_to_f32_tap(const void* src, int src_is_bf16, int ld_src, float* dst, long long rows, int cols, cudaStream_t st);
+// perm != 0: column c is read from the head-padded position scc_pos(c)
+int launch_f32_to_f32_tap(const void* src, int src_is_bf16, int ld_src, float* dst, long long rows, int cols, int perm, cudaStream_t st);
 // out_bf16[N,192] = bf16(a + b) (fusion disabled path, hit_sir_pro.py:1153)
 int launch_add_to_bf16(const float* a, const float* b, bf16* out, long long N, cudaStream_t st);
 
@@ -46,12 +47,28 @@ int launch_sca_mlp(const float* part_sum, const float* part_max, int nparts, Pad
 int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, const float* cmax, const float* s1, const float* s2,
                      CasaW w, bf16* t, cudaStream_t st);
 
-// ---- scc.cu (SCC.forward without proj, hit_sir_pro.py:542-596) --------------------------------
+// ---- scc_umma.cu (SCC.forward without proj, hit_sir_pro.py:542-596) ---------------------------
+// Head-padded token layout of the window tokens T and of the SCC output: reference channel
+// c = half*90 + head*15 + j (half 0 = q / out_s, half 1 = v / out_c, :569-570, :596) sits at position
+// half*96 + head*16 + j.  Position 15 of T holds the constant 1 (bias rider), all other pads are 0.
+__host__ __device__ inline int scc_pos(int c) { const int half = c / kHalf, r = c - half * kHalf; return half * 96 + (r / kHd) * 16 + r % kHd; }
+__host__ __device__ inline int scc_chan(int p) { const int half = p / 96, r = p - half * 96; return (r & 15) == 15 ? -1 : half * kHalf + (r >> 4) * kHd + (r & 15); }
+// Token tiles of a window: bx x by pixels = TT tokens (TMA box), row-major tiles_x x (tiles/tiles_x) per window
+struct SccTile { int bx, by, TT, tiles_x, tiles; };
+__host__ __device__ inline SccTile scc_tile(int w) {
+  if (w == 4) return SccTile{4, 4, 16, 1, 1};
+  if (w == 8) return SccTile{8, 8, 64, 1, 1};
+  if (w >= 16 && w <= 64 && w % 16 == 0) return SccTile{16, 8, 128, w / 16, (w / 16) * (w / 8)};
+  return SccTile{0, 0, 0, 0, 0};
+}
 struct SccW {
   const float* wk1; const float* bk1;    // k_generate1 [15][15], [15]
   const float* wk2; const float* bk2;    // k_generate2
   const float* wsl; float* bsl_dev;      // spatial_linear weight [r*r]; bias read from device (1 float)
   const float* bias_tbl;                 // pooled relative-position bias [6][L][Lb]
+  const uint8_t* pool_img;               // weights-only UMMA operand images (scc_umma.cu)
+  const uint8_t* bias_img;
+  const uint8_t* w_img;
 };
 struct SccGeom {
   PadGeom pg;
@@ -60,8 +77,12 @@ struct SccGeom {
   int nWy, nWx;        // windows per image
   int parts;           // CTAs per window in the two-phase path (L / 256), 1 for the fused path
 };
-int scc_workspace_floats(const SccGeom& g, long long* partial_floats, long long* final_floats);
-int launch_scc(const bf16* t, const SccGeom& g, const SccW& w, float* partials, float* finals, bf16* out, cudaStream_t st);
+size_t scc_pool_image_bytes(int w);
+size_t scc_bias_image_bytes(int w);
+int launch_scc_images(const SccW& w, int win, int base, uint8_t* pool_img, uint8_t* bias_img, uint8_t* w_img, cudaStream_t st);
+// dbg (optional): fp32 dump of window 0: G[128][192] | TPT[192][64] | corr[128][96] | KP[128][96] | Mblk[128][16]
+constexpr int kSccDbgFloats = 63488;
+int launch_scc_umma(const bf16* t, const SccGeom& g, const SccW& w, bf16* out, float* dbg, int num_sms, cudaStream_t st);
 
 // ---- fusion (UnionAttention / Fusion, hit_sir_pro.py:104-162) -------------------------------------
 struct UaW {
@@ -85,7 +106,8 @@ int launch_fusion_combine(const float* first, const float* second, const float* 
 
 // ---- pack.cu (weight-only precomputation) --------------------------------------------------------
 // conv / linear weight fp32 [Co][Ci][kh][kw] -> bf16 [Npad][taps*Cipad], k = tap*Cipad + ci; bias -> fp32 [Npad]
-int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, cudaStream_t st);
+// perm_k != 0 (linear only): K index = head-padded position, i.e. wp[n][p] = w[n][scc_chan(p)]
+int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, int perm_k, cudaStream_t st);
 // MultipleSizeConvExtract: conv3/5/7/9 + conv_x embedded in a 9x9x3 footprint, rows grouped per 36 channels (EPI_MSGATE)
 int launch_pack_msconv(const float* w3, const float* w5, const float* w7, const float* w9, const float* wx,
                        const float* b3, const float* b5, const float* b7, const float* b9, const float* bx,

@@ -14,14 +14,15 @@ inline int grid_for(long long total, int block) {
 }
 
 __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp, float* __restrict__ bp,
-                                 int Co, int Ci, int taps, int Npad, int Cipad) {
+                                 int Co, int Ci, int taps, int Npad, int Cipad, int perm_k) {
   const long long K = (long long)taps * Cipad;
   const long long total = (long long)Npad * K;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(idx / K); const int k = (int)(idx - (long long)n * K);
     const int tap = k / Cipad, ci = k - tap * Cipad;
     float v = 0.f;
-    if (n < Co && ci < Ci) v = w[((long long)n * Ci + ci) * taps + tap];     // [Co][Ci][kh][kw], tap = kh*kw_size + kw
+    const int cs = perm_k ? scc_chan(ci) : (ci < Ci ? ci : -1);
+    if (n < Co && cs >= 0) v = w[((long long)n * Ci + cs) * taps + tap];     // [Co][Ci][kh][kw], tap = kh*kw_size + kw
     wp[idx] = __float2bfloat16(v);
   }
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < Npad; n += gridDim.x * blockDim.x) bp[n] = (n < Co && b != nullptr) ? b[n] : 0.f;
@@ -139,8 +140,8 @@ __global__ void pooled_bias_kernel(const float* __restrict__ tbl, int win, int b
 
 }  // namespace
 
-int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, cudaStream_t st) {
-  pack_conv_kernel<<<grid_for((long long)Npad * taps * Cipad, 256), 256, 0, st>>>(w, b, wp, bp, Co, Ci, taps, Npad, Cipad);
+int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, int perm_k, cudaStream_t st) {
+  pack_conv_kernel<<<grid_for((long long)Npad * taps * Cipad, 256), 256, 0, st>>>(w, b, wp, bp, Co, Ci, taps, Npad, Cipad, perm_k);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
