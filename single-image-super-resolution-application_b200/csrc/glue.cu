@@ -2,6 +2,7 @@
 // contraction or the window self-correlation): entry im2col, LayerNorm, depthwise 5x5 + GELU,
 // casa (SpatialChannelAttention) statistics and gating, UnionAttention/Fusion statistics and
 // gating, nearest upsampling.  Token-major (NHWC) throughout; 128-bit accesses where rows allow.
+#include "gemm.cuh"
 #include "kernels.cuh"
 
 namespace hitsir {
@@ -68,88 +69,80 @@ __global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restr
 }
 
 // h2 = h1 + gelu(dw5x5(h1) + b)   (ConvFFN middle, hit_sir_pro.py:42 with :15-17).
-// CTA = 8 x 32 pixel tile x 64 channels.  The (8+4) x (32+4) x 64 bf16 input patch is staged once in shared
-// memory (zero halo = the conv's zero padding); thread = (row, 4 consecutive x, 8 channels) x 2 passes: 8 input
-// vectors per filter row feed 4 outputs, filter taps are re-read from smem once per filter row; packed fp32 FMA.
-constexpr int kDwTH = 8, kDwTW = 32, kDwCC = 64;
-constexpr int kDwPW = kDwTW + 4, kDwPH = kDwTH + 4;
+// CTA = 16 x 32 pixel tile x 64 channels.  One TMA box load stages the (16+4) x (32+4) x 64 bf16 input patch (the
+// conv's zero padding = TMA out-of-bounds fill).  A warp owns a 4 x 4 output block across the 64 channels (lane = channel
+// pair, so every shared-memory access is one conflict-free 128-byte pixel row); the 25 taps of the lane's channel pair
+// live in registers, each input word is loaded once per block and feeds up to 20 packed FMAs.
+constexpr int kDwTH = 16, kDwTW = 32, kDwPH = kDwTH + 4, kDwPW = kDwTW + 4;
+constexpr int kDwTileBytes = kDwPH * kDwPW * 128;
 
-__global__ void __launch_bounds__(256, 2) dwconv5_tiled_kernel(const bf16* __restrict__ h1, const float* __restrict__ wt, const float* __restrict__ bias,
-                                                            bf16* __restrict__ h2, int B, int H, int W, int tiles_x, int tiles_y) {
-  extern __shared__ __align__(16) uint8_t dw_smem[];
-  uint4* tile = reinterpret_cast<uint4*>(dw_smem);                       // [kDwPH*kDwPW][8] x 16 B
-  float* w_s = reinterpret_cast<float*>(dw_smem + kDwPH * kDwPW * 128);   // [25][64]
-  float* b_s = w_s + 25 * kDwCC;                                          // [64]
-  const int cchunk = blockIdx.y;                       // 64-channel slice
+__global__ void __launch_bounds__(256, 2) dwconv5_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ wt,
+                                                         const float* __restrict__ bias, bf16* __restrict__ h2, int B, int H, int W,
+                                                         int tiles_x, int tiles_y) {
+  extern __shared__ __align__(128) uint8_t dw_smem[];
+  const uint32_t tile_s = smem_u32(dw_smem);
+  const uint32_t bar = tile_s + kDwTileBytes;
+  const int cchunk = blockIdx.y;
   const int tx = blockIdx.x % tiles_x; const int t2 = blockIdx.x / tiles_x;
   const int ty = t2 % tiles_y; const int b = t2 / tiles_y;
   const int y0 = ty * kDwTH, x0 = tx * kDwTW;
-  const int cbase = cchunk * kDwCC;
-  for (int i = threadIdx.x; i < 25 * kDwCC; i += 256) w_s[i] = wt[(i / kDwCC) * kHidp + cbase + (i % kDwCC)];
-  if (threadIdx.x < kDwCC) b_s[threadIdx.x] = bias[cbase + threadIdx.x];
-  for (int i = threadIdx.x; i < kDwPH * kDwPW * 8; i += 256) {
-    const int ch = i & 7, pp = i >> 3;
-    const int py = pp / kDwPW, px = pp - py * kDwPW;
-    const int yy = y0 + py - 2, xx = x0 + px - 2;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-      v = __ldg(reinterpret_cast<const uint4*>(h1 + (((long long)b * H + yy) * W + xx) * kHidp + cbase) + ch);
-    tile[i] = v;
-  }
+  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
   __syncthreads();
-  const int grp = threadIdx.x & 7;                     // 8-channel group inside the 64-channel slice
-  const int row = threadIdx.x >> 5;                    // tile row
-  const int y = y0 + row;
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, kDwTileBytes);
+    tma_load_4d(tile_s, &tm_in, bar, cchunk * 64, x0 - 2, y0 - 2, b);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = cchunk * 64 + 2 * lane;
+  float2 w[25];
+#pragma unroll
+  for (int t = 0; t < 25; ++t) w[t] = *reinterpret_cast<const float2*>(wt + t * kHidp + c);
+  const float2 bs = *reinterpret_cast<const float2*>(bias + c);
+  const bool live = c < kHid;                       // kHid is even: a channel pair is entirely real or entirely padding
+  mbar_wait(bar, 0);
+  const uint32_t* tile = reinterpret_cast<const uint32_t*>(dw_smem) + lane;      // + pixel * 32 words
 #pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {
-    const int xq = ((threadIdx.x >> 3) & 3) + 4 * pass;  // which run of 4 pixels along x (8 runs per tile row)
+  for (int pass = 0; pass < 4; ++pass) {
+    const int blk = warp * 4 + pass;                // 4 x 8 blocks of 4 x 4 pixels
+    const int by = (blk >> 3) * 4, bx = (blk & 7) * 4;
     float2 acc[4][4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o)
+    for (int oy = 0; oy < 4; ++oy)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[o][j] = make_float2(b_s[grp * 8 + 2 * j], b_s[grp * 8 + 2 * j + 1]);
-#pragma unroll 1
-    for (int ky = 0; ky < 5; ++ky) {
-      float2 wr[5][4];
+      for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = bs;
+    uint32_t center[4][4];
 #pragma unroll
-      for (int kx = 0; kx < 5; ++kx) {
-        const float4 a = *reinterpret_cast<const float4*>(w_s + (ky * 5 + kx) * kDwCC + grp * 8);
-        const float4 c = *reinterpret_cast<const float4*>(w_s + (ky * 5 + kx) * kDwCC + grp * 8 + 4);
-        wr[kx][0] = make_float2(a.x, a.y); wr[kx][1] = make_float2(a.z, a.w);
-        wr[kx][2] = make_float2(c.x, c.y); wr[kx][3] = make_float2(c.z, c.w);
+    for (int iy = 0; iy < 8; ++iy) {
+      float2 in[8];
+#pragma unroll
+      for (int ix = 0; ix < 8; ++ix) {
+        const uint32_t u = tile[((by + iy) * kDwPW + bx + ix) * 32];
+        in[ix] = unpack_bf16x2(u);
+        if (iy >= 2 && iy < 6 && ix >= 2 && ix < 6) center[iy - 2][ix - 2] = u;
       }
 #pragma unroll
-      for (int xi = 0; xi < 8; ++xi) {
-        const uint4 u = tile[((row + ky) * kDwPW + xq * 4 + xi) * 8 + grp];
-        const float2 v[4] = {unpack_bf16x2(u.x), unpack_bf16x2(u.y), unpack_bf16x2(u.z), unpack_bf16x2(u.w)};
+      for (int ky = 0; ky < 5; ++ky) {
+        const int oy = iy - ky;                     // compile-time after unrolling
+        if (oy >= 0 && oy < 4) {
 #pragma unroll
-        for (int o = 0; o < 4; ++o) {
-          const int kx = xi - o;                       // compile-time after unrolling
-          if (kx >= 0 && kx < 5) {
+          for (int ox = 0; ox < 4; ++ox)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[o][j] = __ffma2_rn(v[j], wr[kx][j], acc[o][j]);
-          }
+            for (int kx = 0; kx < 5; ++kx) acc[oy][ox] = __ffma2_rn(in[ox + kx], w[ky * 5 + kx], acc[oy][ox]);
         }
       }
     }
-    if (y < H) {
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const int x = x0 + xq * 4 + o;
-        if (x >= W) continue;
-        const uint4 u = tile[((row + 2) * kDwPW + xq * 4 + o + 2) * 8 + grp];       // the un-convolved input (residual term)
-        const float2 cv[4] = {unpack_bf16x2(u.x), unpack_bf16x2(u.y), unpack_bf16x2(u.z), unpack_bf16x2(u.w)};
-        float r[8];
+    for (int oy = 0; oy < 4; ++oy) {
+      const int y = y0 + by + oy;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          r[2 * j] = cv[j].x + gelu_fast(acc[o][j].x);
-          r[2 * j + 1] = cv[j].y + gelu_fast(acc[o][j].y);
+      for (int ox = 0; ox < 4; ++ox) {
+        const int x = x0 + bx + ox;
+        if (y < H && x < W) {
+          const float2 cv = unpack_bf16x2(center[oy][ox]);
+          const float2 g = gelu2(acc[oy][ox]);
+          const uint32_t o = live ? pack_bf16x2(cv.x + g.x, cv.y + g.y) : 0u;
+          *reinterpret_cast<uint32_t*>(h2 + (((long long)b * H + y) * W + x) * kHidp + c) = o;
         }
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (cbase + grp * 8 + e >= kHid) r[e] = 0.f;
-        *reinterpret_cast<uint4*>(h2 + (((long long)b * H + y) * W + x) * kHidp + cbase + grp * 8) =
-            make_uint4(pack_bf16x2(r[0], r[1]), pack_bf16x2(r[2], r[3]), pack_bf16x2(r[4], r[5]), pack_bf16x2(r[6], r[7]));
       }
     }
   }
@@ -474,14 +467,16 @@ int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* 
 }
 int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, bf16* h2, int B, int H, int W, cudaStream_t st) {
   static bool configured = false;
-  const int smem = kDwPH * kDwPW * 128 + 25 * kDwCC * 4 + kDwCC * 4;
+  const int smem = kDwTileBytes + 16;
   if (!configured) {
-    HITSIR_CHECK(cudaFuncSetAttribute(dwconv5_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    HITSIR_CHECK(cudaFuncSetAttribute(dwconv5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
+  CUtensorMap tm;
+  if (make_tmap_nhwc_plain(&tm, h1, B, H, W, kHidp, 64, kDwPW, kDwPH)) return 1;
   const int tiles_x = (W + kDwTW - 1) / kDwTW, tiles_y = (H + kDwTH - 1) / kDwTH;
-  dim3 grid(tiles_x * tiles_y * B, kHidp / kDwCC);
-  dwconv5_tiled_kernel<<<grid, 256, smem, st>>>(h1, w, bias, h2, B, H, W, tiles_x, tiles_y);
+  dim3 grid(tiles_x * tiles_y * B, kHidp / 64);
+  dwconv5_kernel<<<grid, 256, smem, st>>>(tm, w, bias, h2, B, H, W, tiles_x, tiles_y);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

@@ -295,7 +295,7 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         } else {
           if (p.act == ACT_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = gelu_fast(v[i]);
+            for (int i = 0; i < 32; i += 2) { const float2 g = gelu2(make_float2(v[i], v[i + 1])); v[i] = g.x; v[i + 1] = g.y; }
           } else if (p.act == ACT_LRELU) {
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i], p.slope);
