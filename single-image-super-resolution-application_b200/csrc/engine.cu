@@ -308,14 +308,20 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
   if (c.is_mult_size_conv_feat_extract) {
     h->first_f = 9; h->first_kp = round_up(81 * ic, 64);
     GemmW& g = h->first;
-    g.BN = 192; g.Npad = 960; g.K = h->first_kp;
+    g.BN = 160; g.Npad = 960; g.K = h->first_kp;
     if (dev_alloc(h, &g.w, (size_t)960 * g.K) || dev_alloc(h, &g.b, 960)) return 1;
     if (launch_pack_msconv(P(h, "conv_first.conv3.weight"), P(h, "conv_first.conv5.weight"), P(h, "conv_first.conv7.weight"),
                            P(h, "conv_first.conv9.weight"), P(h, "conv_first.conv_x.weight"), P(h, "conv_first.conv3.bias"),
                            P(h, "conv_first.conv5.bias"), P(h, "conv_first.conv7.bias"), P(h, "conv_first.conv9.bias"),
                            P(h, "conv_first.conv_x.bias"), g.w, g.b, ic, g.K, st)) return 1;
-    if (make_tmap_2d(&g.tm, g.w, (uint64_t)g.K, 960, (uint64_t)g.K * 2, 64, 192)) return 1;
-    if (make_gemm_w(h, &h->first_last, "conv_first.conv_last", C, 4 * C, 1, st)) return 1;
+    if (make_tmap_2d(&g.tm, g.w, (uint64_t)g.K, 960, (uint64_t)g.K * 2, 64, 160)) return 1;
+    {
+      GemmW& l = h->first_last;
+      l.BN = 192; l.Npad = 192; l.K = 768;
+      if (dev_alloc(h, &l.w, (size_t)192 * 768) || dev_alloc(h, &l.b, 192)) return 1;
+      if (launch_pack_mslast(P(h, "conv_first.conv_last.weight"), P(h, "conv_first.conv_last.bias"), l.w, l.b, 192, st)) return 1;
+      if (make_tmap_2d(&l.tm, l.w, 768, 192, 768 * 2, 64, 192)) return 1;
+    }
   } else {
     h->first_f = 3; h->first_kp = round_up(9 * ic, 64);
     GemmW& g = h->first;
@@ -564,8 +570,9 @@ void base_params(GemmParams& p, const GemmW& w) {
 // The staged-epilogue kernel covers the plain-store and LayerNorm epilogues; the gate / pixel-shuffle
 // epilogues (once per forward) keep the direct-store kernel.
 bool tma_epilogue(const HitsirHandle* h, const GemmW& w, const GemmParams& p) {
-  return !h->simt && !h->direct_epilogue && (p.epi == EPI_STORE || p.epi == EPI_LN) && (w.BN == 192 || w.BN == 64) &&
-         p.out2_f32 == nullptr && w.Npad <= 384;
+  if (h->simt || h->direct_epilogue) return false;
+  if (p.epi == EPI_MSGATE) return w.BN == 160;
+  return (p.epi == EPI_STORE || p.epi == EPI_LN) && (w.BN == 192 || w.BN == 64) && p.out2_f32 == nullptr && w.Npad <= 384;
 }
 
 int run_gemm(Fwd& f, const char* cat, const GemmW& w, GemmParams& p, const CUtensorMap* maps, bool tma) {
@@ -656,7 +663,7 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   base_params(p, bw.fc1);
   p.epi = EPI_STORE; p.act = ACT_GELU; p.n_real = kHid; p.out_bf16 = ws.H1; p.ldb = kHidp;
   RUN(linear(f, "gemm_fc1_gelu", bw.fc1, ws.xb0, f.N, p));
-  LAUNCH("dwconv5", 1, launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, f.st));
+  LAUNCH("dwconv5", 1, launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, h->num_sms, f.st));
   // fc2 + norm2 + residual (:704)
   base_params(p, bw.fc2);
   p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g2; p.beta = bw.b2; p.res = xout; p.ldr = kC;
@@ -697,16 +704,15 @@ int forward_impl(Fwd& f, const float* x, float* y) {
     p.epi = EPI_MSGATE; p.n_real = kC; p.out_bf16 = G; p.ldb = 4 * kCp;
     RUN(linear(f, "gemm_first_msgate", h->first, A0, N, p));
     base_params(p, h->first_last);
-    p.epi = EPI_LN; p.n_real = kC; p.gamma = pe_g; p.beta = pe_b;
-    p.out2_f32 = ws.S; p.ldf2 = kC; p.out_f32 = ws.P; p.ldf = kC;
-    RUN(linear(f, "gemm_first_last_ln", h->first_last, G, N, p));
+    p.epi = EPI_STORE; p.n_real = kC; p.out_f32 = ws.S; p.ldf = kC;
+    RUN(linear(f, "gemm_first_last", h->first_last, G, N, p));
   } else {
-    // the plain conv_first reads A0 (in xb0|xb1) so it must not write a bf16 shadow there
     base_params(p, h->first);
-    p.epi = EPI_LN; p.n_real = kC; p.gamma = pe_g; p.beta = pe_b;
-    p.out2_f32 = ws.S; p.ldf2 = kC; p.out_f32 = ws.P; p.ldf = kC;
-    RUN(linear(f, "gemm_first_ln", h->first, A0, N, p));
+    p.epi = EPI_STORE; p.n_real = kC; p.out_f32 = ws.S; p.ldf = kC;
+    RUN(linear(f, "gemm_first", h->first, A0, N, p));
   }
+  // patch_embed LayerNorm (:975-983): shallow features S stay for the fusion, the stream starts from LN(S)
+  LAUNCH("ln_rows", 1, launch_ln_rows(ws.S, pe_g, pe_b, nullptr, ws.P, N, f.st));
   TAP("shallow", ws.S, 0, kC, N, kC);
   TAP("embed", ws.P, 0, kC, N, kC);
   // ---- deep features: RHTB stack (:1296-1297, :928-936)

@@ -194,39 +194,35 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, Acc& acc, cons
       }
     }
   } else if (p.epi == EPI_MSGATE) {
-    // N tile `n_tile` holds, for the 36 embedding channels c = 36*n_tile + i:
-    //   cols [36k, 36k+36), k=0..3 : conv3/5/7/9 outputs, cols [144,180): conv_x (1x1) output.
-    // g_k = x_k * sigmoid(x_1 * x_k) + x_k  (hit_sir_pro.py:83-92) -> out_bf16[row, k*Cemb + c],
-    // Cemb = p.n_real (embedding width); the concat order is (x3,x5,x7,x9) (:100).
-    // Requires BN == 192.
-    if (ri.valid && n_tile == 0) {   // zero the K padding [4*Cemb, ldb) of the gated concat once per row
-      for (int c = 4 * p.n_real; c < p.ldb; c += 8)
-        *reinterpret_cast<uint4*>(p.out_bf16 + ri.grow * p.ldb + c) = make_uint4(0u, 0u, 0u, 0u);
-    }
-    float x1[36];
+    // N tile `n_tile` (BN == 160) holds, for the 32 embedding channels c = 32*n_tile + i:
+    //   cols [32k, 32k+32), k=0..3 : conv3/5/7/9 outputs, cols [128,160): conv_x (1x1) output.
+    // g_k = x_k * sigmoid(x_1 * x_k) + x_k  (hit_sir_pro.py:83-92) -> out_bf16[row, 128*n_tile + 32*k + i]
+    // (the [tile][slot][channel] order the packed conv_first.conv_last expects, pack.cu pack_mslast_kernel).
+    float x1[32];
     {
       float v[16];
 #pragma unroll
-      for (int c0 = 144; c0 < 192; c0 += 16) {
+      for (int c0 = 128; c0 < 160; c0 += 16) {
         acc.load16(c0, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c0 + i < 180) x1[c0 + i - 144] = v[i] + __ldg(p.bias + n0 + c0 + i);
+        for (int i = 0; i < 16; ++i) x1[c0 + i - 128] = v[i] + __ldg(p.bias + n0 + c0 + i);
       }
     }
 #pragma unroll
-    for (int c0 = 0; c0 < 144; c0 += 16) {
+    for (int c0 = 0; c0 < 128; c0 += 16) {
       float v[16];
       acc.load16(c0, v);
       if (ri.valid) {
+        uint32_t w[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const int col = c0 + i;                 // compile-time after unrolling
-          const int k = col / 36, ci = col - k * 36;
-          const float xk = v[i] + __ldg(p.bias + n0 + col);
-          const float g = xk * sigmoidf_(x1[ci] * xk) + xk;
-          p.out_bf16[ri.grow * p.ldb + k * p.n_real + 36 * n_tile + ci] = __float2bfloat16(g);
+        for (int i = 0; i < 16; i += 2) {
+          const float xa = v[i] + __ldg(p.bias + n0 + c0 + i), xb = v[i + 1] + __ldg(p.bias + n0 + c0 + i + 1);
+          const float ga = xa * sigmoidf_(x1[(c0 + i) & 31] * xa) + xa, gb = xb * sigmoidf_(x1[(c0 + i + 1) & 31] * xb) + xb;
+          w[i >> 1] = pack_bf16x2(ga, gb);
         }
+        uint4* o = reinterpret_cast<uint4*>(p.out_bf16 + ri.grow * p.ldb + 128 * n_tile + c0);
+        o[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        o[1] = make_uint4(w[4], w[5], w[6], w[7]);
       }
     }
   } else {

@@ -69,82 +69,98 @@ __global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restr
 }
 
 // h2 = h1 + gelu(dw5x5(h1) + b)   (ConvFFN middle, hit_sir_pro.py:42 with :15-17).
-// CTA = 16 x 32 pixel tile x 64 channels.  One TMA box load stages the (16+4) x (32+4) x 64 bf16 input patch (the
-// conv's zero padding = TMA out-of-bounds fill).  A warp owns a 4 x 4 output block across the 64 channels (lane = channel
-// pair, so every shared-memory access is one conflict-free 128-byte pixel row); the 25 taps of the lane's channel pair
-// live in registers, each input word is loaded once per block and feeds up to 20 packed FMAs.
+// Persistent CTAs (one per SM, 16 warps) walk (16 x 32 pixel tile, 64-channel slice) work items.  One TMA box load stages the
+// (16+4) x (32+4) x 64 bf16 input patch (the conv's zero padding = TMA out-of-bounds fill) into one of two buffers while the
+// other is being consumed.  A warp owns 4 x 4 output blocks across the 64 channels (lane = channel pair, so every shared-memory
+// access is one conflict-free 128-byte pixel row); the 25 taps of the lane's channel pair live in registers, each input word is
+// loaded once per block and feeds up to 20 packed FMAs.
 constexpr int kDwTH = 16, kDwTW = 32, kDwPH = kDwTH + 4, kDwPW = kDwTW + 4;
 constexpr int kDwTileBytes = kDwPH * kDwPW * 128;
+constexpr int kDwThreads = 512;
 
-__global__ void __launch_bounds__(256, 2) dwconv5_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ wt,
-                                                         const float* __restrict__ bias, bf16* __restrict__ h2, int B, int H, int W,
-                                                         int tiles_x, int tiles_y) {
+__global__ void __launch_bounds__(kDwThreads, 1) dwconv5_kernel(const __grid_constant__ CUtensorMap tm_in, const float* __restrict__ wt,
+                                                                const float* __restrict__ bias, bf16* __restrict__ h2, int B, int H, int W,
+                                                                int tiles_x, int tiles_y, int total) {
   extern __shared__ __align__(128) uint8_t dw_smem[];
   const uint32_t tile_s = smem_u32(dw_smem);
-  const uint32_t bar = tile_s + kDwTileBytes;
-  const int cchunk = blockIdx.y;
-  const int tx = blockIdx.x % tiles_x; const int t2 = blockIdx.x / tiles_x;
-  const int ty = t2 % tiles_y; const int b = t2 / tiles_y;
-  const int y0 = ty * kDwTH, x0 = tx * kDwTW;
-  if (threadIdx.x == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  const uint32_t bar0 = tile_s + 2 * kDwTileBytes;
+  constexpr int kSlices = kHidp / 64;
+  auto issue = [&](int item, int buf) {
+    const int cchunk = item % kSlices; const int t1 = item / kSlices;
+    const int tx = t1 % tiles_x; const int t2 = t1 / tiles_x;
+    const int ty = t2 % tiles_y; const int b = t2 / tiles_y;
+    mbar_expect_tx(bar0 + 8u * buf, kDwTileBytes);
+    tma_load_4d(tile_s + buf * kDwTileBytes, &tm_in, bar0 + 8u * buf, cchunk * 64, tx * kDwTW - 2, ty * kDwTH - 2, b);
+  };
+  if (threadIdx.x == 0) { mbar_init(bar0, 1); mbar_init(bar0 + 8, 1); fence_barrier_init(); }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    mbar_expect_tx(bar, kDwTileBytes);
-    tma_load_4d(tile_s, &tm_in, bar, cchunk * 64, x0 - 2, y0 - 2, b);
-  }
+  if (threadIdx.x == 0 && (int)blockIdx.x < total) issue(blockIdx.x, 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = cchunk * 64 + 2 * lane;
-  float2 w[25];
+  int it = 0;
+  for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    if (threadIdx.x == 0 && item + (int)gridDim.x < total) issue(item + gridDim.x, buf ^ 1);   // freed by the barrier ending iteration it-1
+    const int cchunk = item % kSlices; const int t1 = item / kSlices;
+    const int tx = t1 % tiles_x; const int t2 = t1 / tiles_x;
+    const int ty = t2 % tiles_y; const int b = t2 / tiles_y;
+    const int y0 = ty * kDwTH, x0 = tx * kDwTW;
+    const int c = cchunk * 64 + 2 * lane;
+    float2 w[25];
 #pragma unroll
-  for (int t = 0; t < 25; ++t) w[t] = *reinterpret_cast<const float2*>(wt + t * kHidp + c);
-  const float2 bs = *reinterpret_cast<const float2*>(bias + c);
-  const bool live = c < kHid;                       // kHid is even: a channel pair is entirely real or entirely padding
-  mbar_wait(bar, 0);
-  const uint32_t* tile = reinterpret_cast<const uint32_t*>(dw_smem) + lane;      // + pixel * 32 words
+    for (int t = 0; t < 25; ++t) w[t] = *reinterpret_cast<const float2*>(wt + t * kHidp + c);
+    const float2 bs = *reinterpret_cast<const float2*>(bias + c);
+    const bool live = c < kHid;                     // kHid is even: a channel pair is entirely real or entirely padding
+    const bool full = (y0 + kDwTH <= H) && (x0 + kDwTW <= W);
+    mbar_wait(bar0 + 8u * buf, (uint32_t)((it >> 1) & 1));
+    const uint32_t* tile = reinterpret_cast<const uint32_t*>(dw_smem + buf * kDwTileBytes) + lane;      // + pixel * 32 words
+    bf16* out_tile = h2 + (((long long)b * H + y0) * W + x0) * kHidp + c;
+    const int rowstride = W * kHidp;
 #pragma unroll 1
-  for (int pass = 0; pass < 4; ++pass) {
-    const int blk = warp * 4 + pass;                // 4 x 8 blocks of 4 x 4 pixels
-    const int by = (blk >> 3) * 4, bx = (blk & 7) * 4;
-    float2 acc[4][4];
+    for (int pass = 0; pass < 2; ++pass) {
+      const int blk = warp * 2 + pass;              // 4 x 8 blocks of 4 x 4 pixels
+      const int by = (blk >> 3) * 4, bx = (blk & 7) * 4;
+      float2 acc[4][4];
 #pragma unroll
-    for (int oy = 0; oy < 4; ++oy)
+      for (int oy = 0; oy < 4; ++oy)
 #pragma unroll
-      for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = bs;
-    uint32_t center[4][4];
+        for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = bs;
+      uint32_t center[4][4];
+      const uint32_t* tp = tile + (by * kDwPW + bx) * 32;
 #pragma unroll
-    for (int iy = 0; iy < 8; ++iy) {
-      float2 in[8];
+      for (int iy = 0; iy < 8; ++iy) {
+        float2 in[8];
 #pragma unroll
-      for (int ix = 0; ix < 8; ++ix) {
-        const uint32_t u = tile[((by + iy) * kDwPW + bx + ix) * 32];
-        in[ix] = unpack_bf16x2(u);
-        if (iy >= 2 && iy < 6 && ix >= 2 && ix < 6) center[iy - 2][ix - 2] = u;
+        for (int ix = 0; ix < 8; ++ix) {
+          const uint32_t u = tp[(iy * kDwPW + ix) * 32];
+          in[ix] = unpack_bf16x2(u);
+          if (iy >= 2 && iy < 6 && ix >= 2 && ix < 6) center[iy - 2][ix - 2] = u;
+        }
+#pragma unroll
+        for (int ky = 0; ky < 5; ++ky) {
+          const int oy = iy - ky;                   // compile-time after unrolling
+          if (oy >= 0 && oy < 4) {
+#pragma unroll
+            for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+              for (int kx = 0; kx < 5; ++kx) acc[oy][ox] = __ffma2_rn(in[ox + kx], w[ky * 5 + kx], acc[oy][ox]);
+          }
+        }
       }
+      bf16* ob = out_tile + by * rowstride + bx * kHidp;
 #pragma unroll
-      for (int ky = 0; ky < 5; ++ky) {
-        const int oy = iy - ky;                     // compile-time after unrolling
-        if (oy >= 0 && oy < 4) {
+      for (int oy = 0; oy < 4; ++oy) {
 #pragma unroll
-          for (int ox = 0; ox < 4; ++ox)
-#pragma unroll
-            for (int kx = 0; kx < 5; ++kx) acc[oy][ox] = __ffma2_rn(in[ox + kx], w[ky * 5 + kx], acc[oy][ox]);
+        for (int ox = 0; ox < 4; ++ox) {
+          if (full || (y0 + by + oy < H && x0 + bx + ox < W)) {
+            const float2 cv = unpack_bf16x2(center[oy][ox]);
+            const float2 g = gelu2(acc[oy][ox]);
+            const uint32_t o = live ? pack_bf16x2(cv.x + g.x, cv.y + g.y) : 0u;
+            *reinterpret_cast<uint32_t*>(ob + oy * rowstride + ox * kHidp) = o;
+          }
         }
       }
     }
-#pragma unroll
-    for (int oy = 0; oy < 4; ++oy) {
-      const int y = y0 + by + oy;
-#pragma unroll
-      for (int ox = 0; ox < 4; ++ox) {
-        const int x = x0 + bx + ox;
-        if (y < H && x < W) {
-          const float2 cv = unpack_bf16x2(center[oy][ox]);
-          const float2 g = gelu2(acc[oy][ox]);
-          const uint32_t o = live ? pack_bf16x2(cv.x + g.x, cv.y + g.y) : 0u;
-          *reinterpret_cast<uint32_t*>(h2 + (((long long)b * H + y) * W + x) * kHidp + c) = o;
-        }
-      }
-    }
+    __syncthreads();                                // every warp is done with `buf` before it is refilled (next iteration's issue)
   }
 }
 
@@ -261,7 +277,7 @@ __global__ void qkv_build_kernel(const float* __restrict__ x, PadGeom g, bf16* _
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const int pos = gi * 8 + e, c = scc_chan(pos);
-      o[e] = c >= 0 ? r[c] : (pos == 15 ? 1.0f : 0.f);
+      o[e] = c >= 0 ? r[c] : (pos < 96 ? 1.0f : 0.f);       // q pads carry the constant 1 (k-gen bias rider), v pads 0
     }
     *reinterpret_cast<uint4*>(t + pix * kCp + gi * 8) =
         make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
@@ -293,7 +309,7 @@ __global__ void __launch_bounds__(96) qkv_casa_kernel(const float* __restrict__ 
   const int pos = 2 * threadIdx.x;
   const int cA = scc_chan(pos), cb = scc_chan(pos + 1);
   const int cbs = cb >= 0 ? cb : cA;                    // pad slot: compute a harmless duplicate, overwrite below
-  const float padv = (pos + 1 == 15) ? 1.0f : 0.f;
+  const float padv = (pos + 1 < 96) ? 1.0f : 0.f;     // q pads carry the constant 1 (k-gen bias rider), v pads 0
   float2 w1[9], w2[9];
 #pragma unroll
   for (int tap = 0; tap < 9; ++tap) {
@@ -306,26 +322,42 @@ __global__ void __launch_bounds__(96) qkv_casa_kernel(const float* __restrict__ 
   __syncthreads();
   const int ysrc = reflect_src(yp, g.H);
   const int n = min(kQkvRun, g.Wp - xs);
-  for (int i = 0; i < n; ++i) {
-    const int xp = xs + i;
-    uint32_t packed = 0u;
-    {
-      const float* xr = x + (((long long)b * g.H + ysrc) * g.W + reflect_src(xp, g.W)) * kC;
-      const float2 xv = make_float2(xr[cA], xr[cbs]);
-      float2 a1 = b1, a2 = b2;
+  const float* xrow = x + ((long long)b * g.H + ysrc) * g.W * kC;
+  bf16* trow = t + (((long long)b * g.Hp + yp) * g.Wp + xs) * kCp + pos;
+  // sliding 3x3 window of both statistic maps in registers: columns i, i+1 carried, column i+2 loaded per pixel
+  float a0[3], a1c[3], m0[3], m1c[3];
 #pragma unroll
-      for (int ky = 0; ky < 3; ++ky)
+  for (int ky = 0; ky < 3; ++ky) { a0[ky] = sa[ky][0]; a1c[ky] = sa[ky][1]; m0[ky] = sm[ky][0]; m1c[ky] = sm[ky][1]; }
+  constexpr int kBatch = 8;
+  for (int i0 = 0; i0 < n; i0 += kBatch) {
+    float2 xv[kBatch];
 #pragma unroll
-        for (int kx = 0; kx < 3; ++kx) {
-          const float va = sa[ky][i + kx], vm = sm[ky][i + kx];
-          a1 = __ffma2_rn(w1[ky * 3 + kx], make_float2(va, va), a1);
-          a2 = __ffma2_rn(w2[ky * 3 + kx], make_float2(vm, vm), a2);
-        }
-      const float o0 = xv.x + 0.5f * (lrelu(a1.x, 0.2f) * g1.x + lrelu(a2.x, 0.2f) * g2.x);     // (:345-359)
-      const float o1 = xv.y + 0.5f * (lrelu(a1.y, 0.2f) * g1.y + lrelu(a2.y, 0.2f) * g2.y);
-      packed = pack_bf16x2(o0, cb >= 0 ? o1 : padv);
+    for (int u = 0; u < kBatch; ++u) {
+      const int xp = min(xs + i0 + u, g.Wp - 1);
+      const float* xr = xrow + (long long)reflect_src(xp, g.W) * kC;
+      xv[u] = make_float2(xr[cA], xr[cbs]);
     }
-    *reinterpret_cast<uint32_t*>(t + (((long long)b * g.Hp + yp) * g.Wp + xp) * kCp + pos) = packed;
+#pragma unroll
+    for (int u = 0; u < kBatch; ++u) {
+      const int i = i0 + u;
+      float a2c[3], m2c[3];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) { a2c[ky] = sa[ky][min(i + 2, kQkvRun + 1)]; m2c[ky] = sm[ky][min(i + 2, kQkvRun + 1)]; }
+      float2 acc1 = b1, acc2 = b2;
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        acc1 = __ffma2_rn(w1[ky * 3 + 0], make_float2(a0[ky], a0[ky]), acc1);
+        acc1 = __ffma2_rn(w1[ky * 3 + 1], make_float2(a1c[ky], a1c[ky]), acc1);
+        acc1 = __ffma2_rn(w1[ky * 3 + 2], make_float2(a2c[ky], a2c[ky]), acc1);
+        acc2 = __ffma2_rn(w2[ky * 3 + 0], make_float2(m0[ky], m0[ky]), acc2);
+        acc2 = __ffma2_rn(w2[ky * 3 + 1], make_float2(m1c[ky], m1c[ky]), acc2);
+        acc2 = __ffma2_rn(w2[ky * 3 + 2], make_float2(m2c[ky], m2c[ky]), acc2);
+        a0[ky] = a1c[ky]; a1c[ky] = a2c[ky]; m0[ky] = m1c[ky]; m1c[ky] = m2c[ky];
+      }
+      const float o0 = xv[u].x + 0.5f * (lrelu(acc1.x, 0.2f) * g1.x + lrelu(acc2.x, 0.2f) * g2.x);     // (:345-359)
+      const float o1 = xv[u].y + 0.5f * (lrelu(acc1.y, 0.2f) * g1.y + lrelu(acc2.y, 0.2f) * g2.y);
+      if (i < n) *reinterpret_cast<uint32_t*>(trow + (long long)i * kCp) = pack_bf16x2(o0, cb >= 0 ? o1 : padv);
+    }
   }
 }
 
@@ -334,33 +366,41 @@ __global__ void __launch_bounds__(96) qkv_casa_kernel(const float* __restrict__ 
 //   rows kernel : CTA per (b, y): channel mean/max per pixel + mean/max over W per channel.
 //   cols kernel : CTA per (b, x): mean/max over H per channel.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192) ua_rows_kernel(const float* __restrict__ a, const float* __restrict__ bsrc, int B, int H, int W,
+__global__ void __launch_bounds__(256) ua_rows_kernel(const float* __restrict__ a, const float* __restrict__ bsrc, int B, int H, int W,
                                                       float* __restrict__ cavg, float* __restrict__ cmax, float* __restrict__ wavg, float* __restrict__ wmax) {
-  __shared__ float red_s[6], red_m[6];
+  // CTA per (b, y); warp per pixel (lane = channels lane + 32 i), per-channel row statistics carried in registers
+  __shared__ float s_sum[8][kCp];
+  __shared__ float s_max[8][kCp];
   const int b = blockIdx.x / H, y = blockIdx.x - b * H;
-  const int c = threadIdx.x;
-  const int warp = c >> 5, lane = c & 31;
-  float rs = 0.f, rm = -INFINITY;
-  for (int xw = 0; xw < W; ++xw) {
-    const long long off = (((long long)b * H + y) * W + xw) * kC + c;
-    float v = 0.f;
-    if (c < kC) { v = a[off]; if (bsrc != nullptr) v += bsrc[off]; rs += v; rm = fmaxf(rm, v); }
-    const float ws = warp_sum(c < kC ? v : 0.f);
-    const float wm = warp_max(c < kC ? v : -INFINITY);
-    if (lane == 0) { red_s[warp] = ws; red_m[warp] = wm; }
-    __syncthreads();
-    if (c == 0) {
-      float s = 0.f, m = -INFINITY;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float rs[6], rm[6];
 #pragma unroll
-      for (int i = 0; i < 6; ++i) { s += red_s[i]; m = fmaxf(m, red_m[i]); }
-      cavg[((long long)b * H + y) * W + xw] = s / (float)kC;
-      cmax[((long long)b * H + y) * W + xw] = m;
+  for (int i = 0; i < 6; ++i) { rs[i] = 0.f; rm[i] = -INFINITY; }
+  for (int xw = warp; xw < W; xw += 8) {
+    const long long off = (((long long)b * H + y) * W + xw) * kC;
+    float s = 0.f, m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const int c = lane + 32 * i;
+      if (c < kC) {
+        float v = a[off + c];
+        if (bsrc != nullptr) v += bsrc[off + c];
+        s += v; m = fmaxf(m, v); rs[i] += v; rm[i] = fmaxf(rm[i], v);
+      }
     }
-    __syncthreads();
+    s = warp_sum(s); m = warp_max(m);
+    if (lane == 0) { cavg[((long long)b * H + y) * W + xw] = s / (float)kC; cmax[((long long)b * H + y) * W + xw] = m; }
   }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) { s_sum[warp][lane + 32 * i] = rs[i]; s_max[warp][lane + 32 * i] = rm[i]; }
+  __syncthreads();
+  const int c = threadIdx.x;
   if (c < kC) {
-    wavg[((long long)b * kC + c) * H + y] = rs / (float)W;
-    wmax[((long long)b * kC + c) * H + y] = rm;
+    float s = 0.f, m = -INFINITY;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) { s += s_sum[wv][c]; m = fmaxf(m, s_max[wv][c]); }
+    wavg[((long long)b * kC + c) * H + y] = s / (float)W;
+    wmax[((long long)b * kC + c) * H + y] = m;
   }
 }
 
@@ -408,25 +448,43 @@ __global__ void ua_small_convs_kernel(int B, int H, int W, UaW w, const float* _
     } else if (idx < n1 + n2) {     // conv2 over the (channel, W) plane                 (:124-126)
       const long long i = idx - n1;
       const int b = (int)(i / (kC * W)); const int rem = (int)(i - (long long)b * kC * W);
-      h_att[i] = conv2to1(havg + (long long)b * kC * W, hmax + (long long)b * kC * W, kC, W, rem / W, rem % W, w.c2_w, w.c2_b[0]);
+      h_att[((long long)b * W + rem % W) * kC + rem / W] =      // stored [b][x][c] (channel fastest) for ua_build
+          conv2to1(havg + (long long)b * kC * W, hmax + (long long)b * kC * W, kC, W, rem / W, rem % W, w.c2_w, w.c2_b[0]);
     } else {                        // conv3 over the (channel, H) plane                 (:128-130)
       const long long i = idx - n1 - n2;
       const int b = (int)(i / (kC * H)); const int rem = (int)(i - (long long)b * kC * H);
-      w_att[i] = conv2to1(wavg + (long long)b * kC * H, wmax + (long long)b * kC * H, kC, H, rem / H, rem % H, w.c3_w, w.c3_b[0]);
+      w_att[((long long)b * H + rem % H) * kC + rem / H] =      // stored [b][y][c]
+          conv2to1(wavg + (long long)b * kC * H, wmax + (long long)b * kC * H, kC, H, rem / H, rem % H, w.c3_w, w.c3_b[0]);
     }
   }
 }
 
+// thread = (pixel, 8 channels); h_att [b][x][c], w_att [b][y][c]
 __global__ void ua_build_kernel(int B, int H, int W, const float* __restrict__ c_att, const float* __restrict__ h_att, const float* __restrict__ w_att,
                                 bf16* __restrict__ s) {
-  const long long total = (long long)B * H * W * kCp;
+  constexpr int groups = kCp / 8;
+  const long long total = (long long)B * H * W * groups;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(idx % kCp);
-    const long long pix = idx / kCp;
+    const int gi = (int)(idx % groups);
+    const long long pix = idx / groups;
     const int xw = (int)(pix % W); const long long t = pix / W; const int y = (int)(t % H); const int b = (int)(t / H);
-    float v = 0.f;
-    if (c < kC) v = c_att[pix] + w_att[((long long)b * kC + c) * H + y] + h_att[((long long)b * kC + c) * W + xw];   // (:133)
-    s[idx] = __float2bfloat16(v);
+    const int c0 = gi * 8;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    if (c0 < kC) {
+      const float ca = c_att[pix];
+      const float* wa = w_att + ((long long)b * H + y) * kC + c0;
+      const float* ha = h_att + ((long long)b * W + xw) * kC + c0;
+      const float4 w0 = *reinterpret_cast<const float4*>(wa), h0 = *reinterpret_cast<const float4*>(ha);
+      v[0] = ca + w0.x + h0.x; v[1] = ca + w0.y + h0.y; v[2] = ca + w0.z + h0.z; v[3] = ca + w0.w + h0.w;      // (:133)
+      if (c0 + 4 < kC) {
+        const float4 w1 = *reinterpret_cast<const float4*>(wa + 4), h1 = *reinterpret_cast<const float4*>(ha + 4);
+        v[4] = ca + w1.x + h1.x; v[5] = ca + w1.y + h1.y; v[6] = ca + w1.z + h1.z; v[7] = ca + w1.w + h1.w;
+      }
+    }
+    *reinterpret_cast<uint4*>(s + pix * kCp + c0) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
 
@@ -465,9 +523,9 @@ int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* 
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
-int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, bf16* h2, int B, int H, int W, cudaStream_t st) {
+int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, bf16* h2, int B, int H, int W, int num_sms, cudaStream_t st) {
   static bool configured = false;
-  const int smem = kDwTileBytes + 16;
+  const int smem = 2 * kDwTileBytes + 32;
   if (!configured) {
     HITSIR_CHECK(cudaFuncSetAttribute(dwconv5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
@@ -475,8 +533,10 @@ int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, b
   CUtensorMap tm;
   if (make_tmap_nhwc_plain(&tm, h1, B, H, W, kHidp, 64, kDwPW, kDwPH)) return 1;
   const int tiles_x = (W + kDwTW - 1) / kDwTW, tiles_y = (H + kDwTH - 1) / kDwTH;
-  dim3 grid(tiles_x * tiles_y * B, kHidp / 64);
-  dwconv5_kernel<<<grid, 256, smem, st>>>(tm, w, bias, h2, B, H, W, tiles_x, tiles_y);
+  const long long total = (long long)tiles_x * tiles_y * B * (kHidp / 64);
+  if (total > 2147483647LL) { set_error("launch_dwconv5: too many tiles"); return 1; }
+  const int grid = total < num_sms ? (int)total : num_sms;
+  dwconv5_kernel<<<grid, kDwThreads, smem, st>>>(tm, w, bias, h2, B, H, W, tiles_x, tiles_y, (int)total);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
@@ -527,7 +587,7 @@ int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, con
 }
 int launch_ua_stats(const float* a, const float* b, int B, int H, int W, float* cavg, float* cmax, float* havg, float* hmax, float* wavg, float* wmax,
                     cudaStream_t st) {
-  ua_rows_kernel<<<B * H, 192, 0, st>>>(a, b, B, H, W, cavg, cmax, wavg, wmax);
+  ua_rows_kernel<<<B * H, 256, 0, st>>>(a, b, B, H, W, cavg, cmax, wavg, wmax);
   HITSIR_CHECK(cudaGetLastError());
   ua_cols_kernel<<<B * W, 192, 0, st>>>(a, b, B, H, W, havg, hmax);
   HITSIR_CHECK(cudaGetLastError());
@@ -541,7 +601,7 @@ int launch_ua_small_convs(int B, int H, int W, UaW w, const float* cavg, const f
   return 0;
 }
 int launch_ua_build(int B, int H, int W, const float* c_att, const float* h_att, const float* w_att, bf16* s, cudaStream_t st) {
-  const long long total = (long long)B * H * W * kCp;
+  const long long total = (long long)B * H * W * (kCp / 8);
   ua_build_kernel<<<grid_for(total, 256), 256, 0, st>>>(B, H, W, c_att, h_att, w_att, s);
   HITSIR_CHECK(cudaGetLastError());
   return 0;

@@ -19,7 +19,7 @@ int launch_entry_im2col(const float* x, bf16* a0, int B, int H, int W, int in_ch
 // LayerNorm over rows of fp32 [N,180] -> bf16 [N,192] (pad zero) and/or fp32 [N,180]
 int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* out_bf16, float* out_f32, long long N, cudaStream_t st);
 // depthwise 5x5 (zero pad 2) + bias -> GELU -> + input  (ConvFFN middle, hit_sir_pro.py:42)
-int launch_dwconv5_gelu_add(const bf16* h1, const float* w_tap_major, const float* bias, bf16* h2, int B, int H, int W, cudaStream_t st);
+int launch_dwconv5_gelu_add(const bf16* h1, const float* w_tap_major, const float* bias, bf16* h2, int B, int H, int W, int num_sms, cudaStream_t st);
 // nearest x2 upsample of an NHWC bf16 map with C channels
 int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st);
 int launch_fill_f32(float* p, float v, long long n, cudaStream_t st);
@@ -50,7 +50,7 @@ int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, con
 // ---- scc_umma.cu (SCC.forward without proj, hit_sir_pro.py:542-596) ---------------------------
 // Head-padded token layout of the window tokens T and of the SCC output: reference channel
 // c = half*90 + head*15 + j (half 0 = q / out_s, half 1 = v / out_c, :569-570, :596) sits at position
-// half*96 + head*16 + j.  Position 15 of T holds the constant 1 (bias rider), all other pads are 0.
+// half*96 + head*16 + j.  The q pads of T (positions 16h+15) hold the constant 1 (k-gen bias rider), the v pads are 0.
 __host__ __device__ inline int scc_pos(int c) { const int half = c / kHalf, r = c - half * kHalf; return half * 96 + (r / kHd) * 16 + r % kHd; }
 __host__ __device__ inline int scc_chan(int p) { const int half = p / 96, r = p - half * 96; return (r & 15) == 15 ? -1 : half * kHalf + (r >> 4) * kHd + (r & 15); }
 // Token tiles of a window: bx x by pixels = TT tokens (TMA box), row-major tiles_x x (tiles/tiles_x) per window
@@ -81,7 +81,7 @@ size_t scc_pool_image_bytes(int w);
 size_t scc_bias_image_bytes(int w);
 int launch_scc_images(const SccW& w, int win, int base, uint8_t* pool_img, uint8_t* bias_img, uint8_t* w_img, cudaStream_t st);
 // dbg (optional): fp32 dump of window 0: G[128][192] | TPT[192][64] | corr[128][96] | KP[128][96] | Mblk[128][16]
-constexpr int kSccDbgFloats = 63488;
+constexpr int kSccDbgFloats = 63488 + 32;   // + phase timeline (clock64) of one window
 int launch_scc_umma(const bf16* t, const SccGeom& g, const SccW& w, bf16* out, float* dbg, int num_sms, cudaStream_t st);
 
 // ---- fusion (UnionAttention / Fusion, hit_sir_pro.py:104-162) -------------------------------------
@@ -108,10 +108,12 @@ int launch_fusion_combine(const float* first, const float* second, const float* 
 // conv / linear weight fp32 [Co][Ci][kh][kw] -> bf16 [Npad][taps*Cipad], k = tap*Cipad + ci; bias -> fp32 [Npad]
 // perm_k != 0 (linear only): K index = head-padded position, i.e. wp[n][p] = w[n][scc_chan(p)]
 int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, int perm_k, cudaStream_t st);
-// MultipleSizeConvExtract: conv3/5/7/9 + conv_x embedded in a 9x9x3 footprint, rows grouped per 36 channels (EPI_MSGATE)
+// MultipleSizeConvExtract: conv3/5/7/9 + conv_x embedded in a 9x9x3 footprint, rows grouped per 32 channels x 5 responses (EPI_MSGATE)
 int launch_pack_msconv(const float* w3, const float* w5, const float* w7, const float* w9, const float* wx,
                        const float* b3, const float* b5, const float* b7, const float* b9, const float* bx,
                        bf16* wp, float* bp, int in_ch, int Kp, cudaStream_t st);
+// conv_first.conv_last for the [tile][slot][32 ch] order of the gated concat (EPI_MSGATE output)
+int launch_pack_mslast(const float* w, const float* b, bf16* wp, float* bp, int Npad, cudaStream_t st);
 // first-layer plain conv (f x f footprint over in_ch) -> [192][Kp] with k = (ky*f+kx)*in_ch + ci
 int launch_pack_firstconv(const float* w, const float* b, bf16* wp, float* bp, int Co, int in_ch, int f, int Kp, cudaStream_t st);
 // [C][1][kh][kw] -> [kh*kw][Cpad] fp32 (tap major); used for depthwise 5x5 (C=360->384) and casa 3x3 (1->C)

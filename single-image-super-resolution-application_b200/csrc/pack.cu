@@ -28,17 +28,18 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < Npad; n += gridDim.x * blockDim.x) bp[n] = (n < Co && b != nullptr) ? b[n] : 0.f;
 }
 
-// rows: tile j (0..4) x [slot q (0..4: conv3,5,7,9,conv_x) x 36 channels] (+12 zero rows); K = 9x9 footprint x in_ch
+// rows: tile j (0..5) x slot q (0..4: conv3,5,7,9,conv_x) x 32 embedding channels c = 32j + ci (zero rows for c >= 180);
+// K = 9x9 footprint x in_ch.  One 160-row N tile therefore holds all five responses of 32 channels (EPI_MSGATE).
 __global__ void pack_msconv_kernel(const float* __restrict__ w3, const float* __restrict__ w5, const float* __restrict__ w7, const float* __restrict__ w9,
                                    const float* __restrict__ wx, const float* __restrict__ b3, const float* __restrict__ b5, const float* __restrict__ b7,
                                    const float* __restrict__ b9, const float* __restrict__ bx, bf16* __restrict__ wp, float* __restrict__ bp, int in_ch, int Kp) {
   const long long total = 960LL * Kp;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int n = (int)(idx / Kp), k = (int)(idx - (long long)n * Kp);
-    const int j = n / 192, rem = n - j * 192;
+    const int j = n / 160, rem = n - j * 160;
+    const int q = rem / 32, c = 32 * j + (rem & 31);
     float v = 0.f;
-    if (rem < 180 && k < 81 * in_ch) {
-      const int q = rem / 36, c = 36 * j + (rem - q * 36);
+    if (c < kC && k < 81 * in_ch) {
       const int tap = k / in_ch, ci = k - tap * in_ch;
       const int ky = tap / 9, kx = tap - ky * 9;
       const int s = (q < 4) ? (3 + 2 * q) : 1;        // filter size
@@ -52,15 +53,28 @@ __global__ void pack_msconv_kernel(const float* __restrict__ w3, const float* __
     wp[idx] = __float2bfloat16(v);
   }
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < 960; n += gridDim.x * blockDim.x) {
-    const int j = n / 192, rem = n - j * 192;
+    const int j = n / 160, rem = n - j * 160;
+    const int q = rem / 32, c = 32 * j + (rem & 31);
     float v = 0.f;
-    if (rem < 180) {
-      const int q = rem / 36, c = 36 * j + (rem - q * 36);
+    if (c < kC) {
       const float* src = q == 0 ? b3 : q == 1 ? b5 : q == 2 ? b7 : q == 3 ? b9 : bx;
       v = src[c];
     }
     bp[n] = v;
   }
+}
+
+// conv_first.conv_last (1x1, 4C -> C) for the gated concat stored as [tile j][slot k][ci]: wp[n][j*128 + k*32 + ci] = w[n][k*C + 32j + ci]
+__global__ void pack_mslast_kernel(const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp, float* __restrict__ bp, int Npad) {
+  const long long total = (long long)Npad * 768;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / 768), kk = (int)(idx - (long long)n * 768);
+    const int j = kk >> 7, k = (kk >> 5) & 3, c = 32 * j + (kk & 31);
+    float v = 0.f;
+    if (n < kC && c < kC) v = w[(long long)n * 4 * kC + k * kC + c];
+    wp[idx] = __float2bfloat16(v);
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < Npad; n += gridDim.x * blockDim.x) bp[n] = n < kC ? b[n] : 0.f;
 }
 
 __global__ void pack_firstconv_kernel(const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp, float* __restrict__ bp,
@@ -148,6 +162,11 @@ int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co
 int launch_pack_msconv(const float* w3, const float* w5, const float* w7, const float* w9, const float* wx, const float* b3, const float* b5,
                        const float* b7, const float* b9, const float* bx, bf16* wp, float* bp, int in_ch, int Kp, cudaStream_t st) {
   pack_msconv_kernel<<<grid_for(960LL * Kp, 256), 256, 0, st>>>(w3, w5, w7, w9, wx, b3, b5, b7, b9, bx, wp, bp, in_ch, Kp);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pack_mslast(const float* w, const float* b, bf16* wp, float* bp, int Npad, cudaStream_t st) {
+  pack_mslast_kernel<<<grid_for((long long)Npad * 768, 256), 256, 0, st>>>(w, b, wp, bp, Npad);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

@@ -43,7 +43,11 @@ constexpr int kOffCorr = kOffTPT + 192 * 128;         // bf16 corr [96][2 blocks
 constexpr int kOffMblk = kOffCorr + 2 * kGBlk;        // bf16 Mblk [96][128 B]
 constexpr int kOffW = kOffMblk + kGBlk;               // k-gen operand image [16][128 B]
 constexpr int kOffBars = kOffW + 2048;
-constexpr int kNumBars = 24;
+constexpr int kNumBars = 25;
+// resident mode (one tile per window): stage s keeps its compact token blocks in the first 24 KB of its 48 KB region, head h's bias
+// image sits at kResBias(h); the pool image follows the three G blocks
+constexpr int kOffResPool = kOffG + 3 * kGBlk;
+__host__ __device__ constexpr int res_bias_off(int h, int bias_bytes) { return (h / 3) * kStage + 24576 + (h % 3) * bias_bytes; }
 constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "smem budget");
 
@@ -54,6 +58,9 @@ struct Params {
   int nwin, nWx, nWy;
   int w, bx, by, TT, tiles_x, tiles, ksteps;
   int Lb, streaming;
+  int cell_ksteps;           // ceil(Lb / 16): k-steps of the contractions over pooled cells
+  int resident;              // single-tile windows (w = 4, 8): pool / bias operand images stay in shared memory, tokens are prefetched
+  int blk;                   // byte stride between the three 64-channel blocks of a token stage (kBlk, or TT*128 when resident)
   float invL;
   int pool_bytes, bias_bytes;
   const uint8_t* pool_img;   // [tiles][pool_bytes]
@@ -121,6 +128,24 @@ __device__ __forceinline__ void store16(uint8_t* block, int row, int chunk0, con
       make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]), pack_bf16x2(v[14], v[15]));
 }
 
+// NG x 16 consecutive accumulator columns of this thread's TMEM lane -> registers with a single wait
+template <int NG>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, float (&v)[NG][16]) {
+  uint32_t r[NG][16];
+#pragma unroll
+  for (int i = 0; i < NG; ++i) tmem_ld16_nw(taddr + 16 * i, r[i]);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < NG; ++i) {
+    reg_fence16(r[i]);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[i][e] = __uint_as_float(r[i][e]);
+  }
+}
+
+// optional phase timeline of the third window of CTA 0 (clock64 values, low 24 bits as floats) at dbg[63488 + slot]
+#define SCC_T(slot) do { if (p.dbg != nullptr && blockIdx.x == 0 && wi == 2) p.dbg[63488 + (slot)] = (float)(clock64() & 0xFFFFFF); } while (0)
+
 __global__ void __launch_bounds__(384, 1)
 scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant__ CUtensorMap tm_o, const Params p) {
   extern __shared__ uint8_t smem_raw[];
@@ -136,6 +161,7 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
   auto d_full = [&](int s) { return bar0 + 8u * (18 + s); };
   auto d_empty = [&](int s) { return bar0 + 8u * (20 + s); };
   auto st_ready = [&](int s) { return bar0 + 8u * (22 + s); };
+  const uint32_t res_full = bar0 + 8u * 24;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sp + kOffBars + kNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -143,9 +169,10 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(tok_full(s), 1); mbar_init(tok_empty(s), 1); }
     for (int s = 0; s < kSlots; ++s) { mbar_init(ring_full(s), 1); mbar_init(ring_empty(s), 1); }
-    mbar_init(a_done, 1); mbar_init(mid1_done, 256); mbar_init(mid2_ready, 1); mbar_init(mid3_done, 256);
-    mbar_init(mid4_ready, 1); mbar_init(mid5_done, 256);
-    for (int s = 0; s < 2; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 256); mbar_init(st_ready(s), 256); }
+    mbar_init(a_done, 1); mbar_init(mid1_done, 8); mbar_init(mid2_ready, 1); mbar_init(mid3_done, 8);
+    mbar_init(mid4_ready, 1); mbar_init(mid5_done, 8);
+    mbar_init(res_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(d_full(s), 1); mbar_init(d_empty(s), 8); mbar_init(st_ready(s), 8); }
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
@@ -168,7 +195,7 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
         wait_bar(tok_empty(s), ((tok_cnt >> 1) & 1u) ^ 1u);
         mbar_expect_tx(tok_full(s), (uint32_t)(p.TT * 128 * 3));
 #pragma unroll
-        for (int blk = 0; blk < 3; ++blk) tma_load_4d(sb + s * kStage + blk * kBlk, &tm_t, tok_full(s), blk * 64, x0, y0, b);
+        for (int blk = 0; blk < 3; ++blk) tma_load_4d(sb + s * kStage + blk * p.blk, &tm_t, tok_full(s), blk * 64, x0, y0, b);
         ++tok_cnt;
       };
       auto load_chunk = [&](const uint8_t* src, uint32_t bytes) {
@@ -178,6 +205,16 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
         bulk_load(sb + kOffRing + r * kSlot, src, bytes, ring_full(r));
         ++ring_cnt;
       };
+      if (p.resident) {
+        mbar_expect_tx(res_full, (uint32_t)(p.pool_bytes + kHeads * p.bias_bytes));
+        bulk_load(sb + kOffResPool, p.pool_img, (uint32_t)p.pool_bytes, res_full);
+        for (int h = 0; h < kHeads; ++h)
+          bulk_load(sb + res_bias_off(h, p.bias_bytes), p.bias_img + (size_t)h * p.bias_bytes, (uint32_t)p.bias_bytes, res_full);
+        for (int win = blockIdx.x; win < p.nwin; win += gridDim.x) {
+          const int wx = win % p.nWx; const int t2 = win / p.nWx; const int wy = t2 % p.nWy; const int b = t2 / p.nWy;
+          load_tokens(b, wx * p.w, wy * p.w);          // runs ahead by one window (two stages)
+        }
+      } else
       for (int win = blockIdx.x; win < p.nwin; win += gridDim.x, ++wi) {
         const int wx = win % p.nWx; const int t2 = win / p.nWx; const int wy = t2 % p.nWy; const int b = t2 / p.nWy;
         for (int t = 0; t < p.tiles; ++t) {
@@ -206,59 +243,72 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
       constexpr uint32_t id_oc = make_idesc(128, 96, 0, 0);      // V corr^T
       uint32_t tok_cnt = 0, ring_cnt = 0, d_cnt = 0;
       int wi = 0;
+      if (p.resident) wait_bar(res_full, 0u);
       for (int win = blockIdx.x; win < p.nwin; win += gridDim.x, ++wi) {
         // the phase-A accumulators overlay both phase-B buffers of the previous window
         for (uint32_t buf = 0; buf < 2; ++buf)
           if (d_cnt > buf) { const uint32_t last = ((d_cnt - 1 - buf) >> 1 << 1) + buf; wait_bar(d_empty((int)buf), (last >> 1) & 1u); }
         tc_fence_after();
         const uint32_t a0 = tok_cnt;
+        SCC_T(0);
         // ---------- phase A
         for (int t = 0; t < p.tiles; ++t) {
           const int s = (int)(tok_cnt & 1u);
           wait_bar(tok_full(s), (tok_cnt >> 1) & 1u);
           const int r = (int)(ring_cnt & 3u);
-          wait_bar(ring_full(r), (ring_cnt >> 2) & 1u);
+          if (!p.resident) wait_bar(ring_full(r), (ring_cnt >> 2) & 1u);
           tc_fence_after();
-          const uint32_t st = sb + s * kStage, pool = sb + kOffRing + r * kSlot;
+          const uint32_t st = sb + s * kStage, pool = p.resident ? sb + kOffResPool : sb + kOffRing + r * kSlot;
           for (int ks = 0; ks < p.ksteps; ++ks) {
             const uint32_t acc = (t | ks) != 0 ? 1u : 0u;
-            const uint64_t da = make_desc(st + ks * 2048, kBlk, 1024);
-            const uint64_t da2 = make_desc(st + 2 * kBlk + ks * 2048, kBlk, 1024);
+            const uint64_t da = make_desc(st + ks * 2048, (uint32_t)p.blk, 1024);
+            const uint64_t da2 = make_desc(st + 2 * p.blk + ks * 2048, (uint32_t)p.blk, 1024);
             const uint64_t dp = kdesc(pool + (ks >> 2) * 8192 + (ks & 3) * 32);
             umma_bf16(tmem + kTmG, da, da, id_G, acc);
             umma_bf16(tmem + kTmTlo, da, dp, id_T, acc);
             umma_bf16(tmem + kTmThi, da2, dp, id_T, acc);
           }
-          umma_commit(ring_empty(r));
+          if (!p.resident) { umma_commit(ring_empty(r)); ++ring_cnt; }
           if (p.streaming) umma_commit(tok_empty(s));
-          ++tok_cnt; ++ring_cnt;
+          ++tok_cnt;
         }
         umma_commit(a_done);
+        SCC_T(1);
         // ---------- mid2: corr = G Wk^T, KP = TPT^T Wk^T (per head: q part, v part, bias via the ones channel)
         wait_bar(mid1_done, (uint32_t)(wi & 1));
         tc_fence_after();
+        SCC_T(2);
         {
+          // every head's q slice carries its own ones column (position 16h+15), so the k-gen bias rides in the q-part contraction.
+          // Issue order interleaves the 12 independent accumulators: back-to-back MMAs never accumulate into the same columns.
           const uint32_t gb = sb + kOffG, tb = sb + kOffTPT, wb = sb + kOffW;
+          const uint64_t w1d = kdesc(wb), w2d = kdesc(wb + 32);
+#pragma unroll
+          for (int h = 0; h < kHeads; ++h) {
+            umma_bf16(tmem + kTmCorr + 16 * h, kdesc(gb + (h >> 2) * kGBlk + (h & 3) * 32), w1d, id_c16, 0u);
+            umma_bf16(tmem + kTmKP + 16 * h, make_desc(tb + 16 * h * 128, 1024, 1024), w1d, id_kp, 0u);
+          }
+#pragma unroll
           for (int h = 0; h < kHeads; ++h) {
             const int cv = 96 + 16 * h;
-            umma_bf16(tmem + kTmCorr + 16 * h, kdesc(gb + (h >> 2) * kGBlk + (h & 3) * 32), kdesc(wb), id_c16, 0u);
-            umma_bf16(tmem + kTmCorr + 16 * h, kdesc(gb + (cv >> 6) * kGBlk + (cv & 63) * 2), kdesc(wb + 32), id_c16, 1u);
-            umma_bf16(tmem + kTmCorr + 16 * h, kdesc(gb), kdesc(wb + 64), id_c16, 1u);
-            umma_bf16(tmem + kTmKP + 16 * h, make_desc(tb + 16 * h * 128, 1024, 1024), kdesc(wb), id_kp, 0u);
-            umma_bf16(tmem + kTmKP + 16 * h, make_desc(sb + kOffKP + 16 * h * 128, 1024, 1024), kdesc(wb + 32), id_kp, 1u);
-            umma_bf16(tmem + kTmKP + 16 * h, make_desc(tb, 1024, 1024), kdesc(wb + 64), id_kp, 1u);
+            umma_bf16(tmem + kTmCorr + 16 * h, kdesc(gb + (cv >> 6) * kGBlk + (cv & 63) * 2), w2d, id_c16, 1u);
+            umma_bf16(tmem + kTmKP + 16 * h, make_desc(sb + kOffKP + 16 * h * 128, 1024, 1024), w2d, id_kp, 1u);
           }
         }
         umma_commit(mid2_ready);
+        SCC_T(3);
         // ---------- mid4: Mfull[(h,j)][(h',i)] = sum_m VPT[(h,j)][m] KP[m][(h',i)]
         wait_bar(mid3_done, (uint32_t)(wi & 1));
         tc_fence_after();
-        for (int ks = 0; ks < 4; ++ks)
+        SCC_T(4);
+        for (int ks = 0; ks < p.cell_ksteps; ++ks)
           umma_bf16(tmem + kTmMblk, kdesc(sb + kOffTPT + 96 * 128 + ks * 32), make_desc(sb + kOffKP + ks * 2048, 8192, 1024), id_mb, ks ? 1u : 0u);
         umma_commit(mid4_ready);
+        SCC_T(5);
         // ---------- phase B
         wait_bar(mid5_done, (uint32_t)(wi & 1));
         tc_fence_after();
+        SCC_T(6);
         for (int t = 0; t < p.tiles; ++t) {
           const uint32_t idx = p.streaming ? tok_cnt : a0 + (uint32_t)t;
           const int s = (int)(idx & 1u);
@@ -267,26 +317,42 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
           wait_bar(d_empty(buf), ((d_cnt >> 1) & 1u) ^ 1u);
           tc_fence_after();
           const uint32_t st = sb + s * kStage, D = tmem + (uint32_t)(buf * 192);
-          for (int h = 0; h < kHeads; ++h) {
-            umma_bf16(D + 16 * h, kdesc(st + (h >> 2) * kBlk + (h & 3) * 32), kdesc(sb + kOffMblk + 16 * h * 128 + (h & 3) * 32), id_c16, 0u);
-            const int r = (int)(ring_cnt & 3u);
-            wait_bar(ring_full(r), (ring_cnt >> 2) & 1u);
-            tc_fence_after();
-            const uint32_t bias = sb + kOffRing + r * kSlot, vp = sb + kOffTPT + (96 + 16 * h) * 128;
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks) umma_bf16(D + 16 * h, kdesc(bias + ks * 32), kdesc(vp + ks * 32), id_c16, 1u);
-            umma_commit(ring_empty(r));
-            ++ring_cnt;
-          }
-#pragma unroll
-          for (int ks = 0; ks < 6; ++ks) {
+          auto corr_step = [&](int ks) {
             const int ch = 96 + 16 * ks;
-            umma_bf16(D + 96, kdesc(st + (ch >> 6) * kBlk + (ch & 63) * 2), kdesc(sb + kOffCorr + ((ch >> 6) - 1) * kGBlk + (ch & 63) * 2), id_oc,
+            umma_bf16(D + 96, kdesc(st + (ch >> 6) * p.blk + (ch & 63) * 2), kdesc(sb + kOffCorr + ((ch >> 6) - 1) * kGBlk + (ch & 63) * 2), id_oc,
                       ks ? 1u : 0u);
+          };
+          if (p.resident) {
+            // all six bias images are resident: interleave the seven independent accumulators (6 heads + out_c)
+#pragma unroll
+            for (int h = 0; h < kHeads; ++h)
+              umma_bf16(D + 16 * h, kdesc(st + (h >> 2) * p.blk + (h & 3) * 32), kdesc(sb + kOffMblk + 16 * h * 128 + (h & 3) * 32), id_c16, 0u);
+            corr_step(0);
+            for (int ks = 0; ks < p.cell_ksteps; ++ks) {
+#pragma unroll
+              for (int h = 0; h < kHeads; ++h)
+                umma_bf16(D + 16 * h, kdesc(sb + res_bias_off(h, p.bias_bytes) + ks * 32), kdesc(sb + kOffTPT + (96 + 16 * h) * 128 + ks * 32), id_c16, 1u);
+              if (ks + 1 < 6) corr_step(ks + 1);
+            }
+            for (int ks = p.cell_ksteps + 1; ks < 6; ++ks) corr_step(ks);
+          } else {
+            for (int h = 0; h < kHeads; ++h) {
+              umma_bf16(D + 16 * h, kdesc(st + (h >> 2) * p.blk + (h & 3) * 32), kdesc(sb + kOffMblk + 16 * h * 128 + (h & 3) * 32), id_c16, 0u);
+              corr_step(h);
+              const int r = (int)(ring_cnt & 3u);
+              wait_bar(ring_full(r), (ring_cnt >> 2) & 1u);
+              tc_fence_after();
+              const uint32_t bias = sb + kOffRing + r * kSlot, vp = sb + kOffTPT + (96 + 16 * h) * 128;
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) umma_bf16(D + 16 * h, kdesc(bias + ks * 32), kdesc(vp + ks * 32), id_c16, 1u);
+              umma_commit(ring_empty(r));
+              ++ring_cnt;
+            }
           }
           umma_commit(d_full(buf));
           ++d_cnt;
         }
+        SCC_T(7);
       }
     }
   } else if (warp == 3) {
@@ -304,7 +370,7 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
           const int x0 = wx * p.w + (t % p.tiles_x) * p.bx, y0 = wy * p.w + (t / p.tiles_x) * p.by;
           if (x0 < p.W && y0 < p.H) {                 // tiles entirely inside the reflect padding are cropped (:696)
 #pragma unroll
-            for (int blk = 0; blk < 3; ++blk) tma_store_4d(&tm_o, sb + s * kStage + blk * kBlk, blk * 64, x0, y0, b);
+            for (int blk = 0; blk < 3; ++blk) tma_store_4d(&tm_o, sb + s * kStage + blk * p.blk, blk * 64, x0, y0, b);
             tma_commit();
             tma_wait_read0();
           }
@@ -328,14 +394,15 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
       // ---------- mid1: G, TPT -> bf16 operand images
       wait_bar(a_done, par);
       tc_fence_after();
+      if (threadIdx.x == 128) SCC_T(8);
       if (q < 3) {
-#pragma unroll 1
+        float v[6][16];
+        tmem_ld_cols<6>(tl + kTmG + hs * 96, v);
+#pragma unroll
         for (int i = 0; i < 6; ++i) {
           const int c0 = hs * 96 + 16 * i;
-          float v[16];
-          tmem_ld16(tl + kTmG + c0, v);
-          store16(sp + kOffG + (c0 >> 6) * kGBlk, row, (c0 & 63) >> 3, v);
-          if (dbg) for (int e = 0; e < 16; ++e) dbg[row * 192 + c0 + e] = v[e];
+          store16(sp + kOffG + (c0 >> 6) * kGBlk, row, (c0 & 63) >> 3, v[i]);
+          if (dbg) for (int e = 0; e < 16; ++e) dbg[row * 192 + c0 + e] = v[i][e];
         }
       }
       if (hs == 0 || q < 2) {
@@ -343,70 +410,74 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
         const uint32_t src = tl + (hs == 0 ? kTmTlo : kTmThi);
         const bool vrow = crow >= 96;
         const bool padrow = ((crow - 96) & 15) == 15;
-#pragma unroll 1
+        float v[4][16];
+        tmem_ld_cols<4>(src, v);
+#pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float v[16];
-          tmem_ld16(src + 16 * i, v);
           if (vrow) {
             // raw pooled v rows feed the k-gen contraction (KP) from ring slot 3; the TPT image keeps vp = pooled v + bsl
-            store16(sp + kOffKP, crow - 96, 2 * i, v);
+            store16(sp + kOffKP, crow - 96, 2 * i, v[i]);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[e] = (16 * i + e < p.Lb && !padrow) ? v[e] + bsl : 0.f;
+            for (int e = 0; e < 16; ++e) v[i][e] = (16 * i + e < p.Lb && !padrow) ? v[i][e] + bsl : 0.f;
           }
-          store16(sp + kOffTPT, crow, 2 * i, v);
-          if (dbg) for (int e = 0; e < 16; ++e) dbg[24576 + crow * 64 + 16 * i + e] = v[e];
+          store16(sp + kOffTPT, crow, 2 * i, v[i]);
+          if (dbg) for (int e = 0; e < 16; ++e) dbg[24576 + crow * 64 + 16 * i + e] = v[i][e];
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(mid1_done);
+      mbar_arrive_warp(mid1_done);
+      if (threadIdx.x == 128) SCC_T(9);
       // ---------- mid3: corr, KP -> bf16 operand images
       wait_bar(mid2_ready, par);
       tc_fence_after();
+      if (threadIdx.x == 128) SCC_T(10);
       if (q < 3) {
-#pragma unroll 1
+        float v[3][16];
+        tmem_ld_cols<3>(tl + kTmCorr + hs * 48, v);
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int c0 = hs * 48 + 16 * i, ch = 96 + c0;
-          float v[16];
-          tmem_ld16(tl + kTmCorr + c0, v);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] *= p.invL;
-          store16(sp + kOffCorr + ((ch >> 6) - 1) * kGBlk, row, (ch & 63) >> 3, v);
-          if (dbg) for (int e = 0; e < 16; ++e) dbg[36864 + row * 96 + c0 + e] = v[e];
+          for (int e = 0; e < 16; ++e) v[i][e] *= p.invL;
+          store16(sp + kOffCorr + ((ch >> 6) - 1) * kGBlk, row, (ch & 63) >> 3, v[i]);
+          if (dbg) for (int e = 0; e < 16; ++e) dbg[36864 + row * 96 + c0 + e] = v[i][e];
         }
       }
       if (q < 2) {
-#pragma unroll 1
+        float v[3][16];
+        tmem_ld_cols<3>(tl + kTmKP + hs * 48, v);
+#pragma unroll
         for (int i = 0; i < 3; ++i) {
           const int c0 = hs * 48 + 16 * i;
-          float v[16];
-          tmem_ld16(tl + kTmKP + c0, v);
 #pragma unroll
-          for (int e = 0; e < 16; ++e) v[e] = (row < p.Lb && e != 15) ? v[e] + bsl : 0.f;
-          store16(sp + kOffKP + (c0 >> 6) * 8192, row, (c0 & 63) >> 3, v);
-          if (dbg) for (int e = 0; e < 16; ++e) dbg[49152 + row * 96 + c0 + e] = v[e];
+          for (int e = 0; e < 16; ++e) v[i][e] = (row < p.Lb && e != 15) ? v[i][e] + bsl : 0.f;
+          store16(sp + kOffKP + (c0 >> 6) * 8192, row, (c0 & 63) >> 3, v[i]);
+          if (dbg) for (int e = 0; e < 16; ++e) dbg[49152 + row * 96 + c0 + e] = v[i][e];
         }
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(mid3_done);
+      mbar_arrive_warp(mid3_done);
+      if (threadIdx.x == 128) SCC_T(11);
       // ---------- mid5: diagonal blocks of Mfull / 15 -> Mblk operand image
       wait_bar(mid4_ready, par);
       tc_fence_after();
+      if (threadIdx.x == 128) SCC_T(12);
       if (hs == 0 && q < 3) {
-        float v[32];
-        tmem_ld16(tl + kTmMblk + 32 * q, v);
-        tmem_ld16(tl + kTmMblk + 32 * q + 16, v + 16);
+        float v[2][16];
+        tmem_ld_cols<2>(tl + kTmMblk + 32 * q, v);
         const int h = row >> 4;
         float o[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) o[e] = ((lane & 16) ? v[16 + e] : v[e]) * (1.0f / 15.0f);
+        for (int e = 0; e < 16; ++e) o[e] = ((lane & 16) ? v[1][e] : v[0][e]) * (1.0f / 15.0f);
         store16(sp + kOffMblk, row, 2 * (h & 3), o);
         if (dbg) for (int e = 0; e < 16; ++e) dbg[61440 + row * 16 + e] = o[e];
       }
       tc_fence_before();
       fence_proxy_async_smem();
-      mbar_arrive(mid5_done);
+      mbar_arrive_warp(mid5_done);
+      if (threadIdx.x == 128) SCC_T(13);
       // ---------- phase B epilogue: accumulator -> bf16, in place over the consumed token tile, then TMA store
       const uint32_t a0 = tok_cnt;
       for (int t = 0; t < p.tiles; ++t) {
@@ -415,18 +486,25 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
         const int buf = (int)(d_cnt & 1u);
         wait_bar(d_full(buf), (d_cnt >> 1) & 1u);
         tc_fence_after();
+        if (threadIdx.x == 128) SCC_T(14);
         uint8_t* stp = sp + s * kStage;
-#pragma unroll 1
-        for (int i = 0; i < 6; ++i) {
-          const int c0 = hs * 96 + 16 * i;
-          float v[16];
-          tmem_ld16(tl + (uint32_t)(buf * 192) + c0, v);
-          store16(stp + (c0 >> 6) * kBlk, row, (c0 & 63) >> 3, v);
+        {
+          float v[6][16];
+          tmem_ld_cols<6>(tl + (uint32_t)(buf * 192 + hs * 96), v);
+          tc_fence_before();
+          mbar_arrive_warp(d_empty(buf));                    // accumulator is in registers: the next tile's MMAs may overwrite it
+#pragma unroll
+          if (row < p.TT) {                             // compact (resident) stages hold only TT rows per block
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+              const int c0 = hs * 96 + 16 * i;
+              store16(stp + (c0 >> 6) * p.blk, row, (c0 & 63) >> 3, v[i]);
+            }
+          }
         }
-        tc_fence_before();
-        mbar_arrive(d_empty(buf));
         fence_proxy_async_smem();
-        mbar_arrive(st_ready(s));
+        mbar_arrive_warp(st_ready(s));
+        if (threadIdx.x == 128) SCC_T(15);
         ++d_cnt;
       }
       tok_cnt = a0 + (uint32_t)(mult * p.tiles);
@@ -484,7 +562,8 @@ __global__ void scc_bias_image_kernel(const float* __restrict__ tbl, int w, int 
   }
 }
 
-// [16 rows o][64 k]: k<16: W1[o][k]/2, 16<=k<32: W2[o][k-16]/2, k==47: (bk1[o]+bk2[o])/2 (rides on the ones channel); row 15 = 0
+// [16 rows o][64 k]: k<15: W1[o][k]/2, k==15: (bk1[o]+bk2[o])/2 (rides on the ones column of every head's q slice),
+// 16<=k<31: W2[o][k-16]/2; row 15 = 0
 __global__ void scc_w_image_kernel(const float* __restrict__ w1, const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
                                    uint8_t* __restrict__ img) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -493,8 +572,8 @@ __global__ void scc_w_image_kernel(const float* __restrict__ w1, const float* __
   float v = 0.f;
   if (o < kHd) {
     if (k < kHd) v = 0.5f * w1[o * kHd + k];
+    else if (k == 15) v = 0.5f * (b1[o] + b2[o]);
     else if (k >= 16 && k < 16 + kHd) v = 0.5f * w2[o * kHd + (k - 16)];
-    else if (k == 47) v = 0.5f * (b1[o] + b2[o]);
   }
   *reinterpret_cast<bf16*>(img + swz_elem(o, k)) = __float2bfloat16(v);
 }
@@ -536,6 +615,9 @@ int launch_scc_umma(const bf16* t, const SccGeom& g, const SccW& w, bf16* out, f
   p.nwin = g.pg.B * g.nWy * g.nWx; p.nWx = g.nWx; p.nWy = g.nWy;
   p.w = g.w; p.bx = tg.bx; p.by = tg.by; p.TT = tg.TT; p.tiles_x = tg.tiles_x; p.tiles = tg.tiles; p.ksteps = tg.TT / 16;
   p.Lb = g.Lb; p.streaming = tg.tiles > 2 ? 1 : 0;
+  p.cell_ksteps = (g.Lb + 15) / 16;
+  p.resident = tg.tiles == 1 ? 1 : 0;
+  p.blk = p.resident ? tg.TT * 128 : kBlk;
   p.invL = 1.0f / (float)g.L;
   p.pool_bytes = (tg.TT > 64 ? tg.TT / 64 : 1) * 8192;
   p.bias_bytes = tg.TT * 128;

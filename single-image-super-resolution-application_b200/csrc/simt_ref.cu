@@ -56,6 +56,7 @@ int launch_simt_gemm(int BN, const GemmParams& p, cudaStream_t st) {
     case 32: simt_gemm_kernel<32><<<grid, 128, 0, st>>>(p); break;
     case 48: simt_gemm_kernel<48><<<grid, 128, 0, st>>>(p); break;
     case 64: simt_gemm_kernel<64><<<grid, 128, 0, st>>>(p); break;
+    case 160: simt_gemm_kernel<160><<<grid, 128, 0, st>>>(p); break;
     case 192: simt_gemm_kernel<192><<<grid, 128, 0, st>>>(p); break;
     case 256: simt_gemm_kernel<256><<<grid, 128, 0, st>>>(p); break;
     default: set_error("launch_simt_gemm: unsupported N tile %d", BN); return 1;

@@ -262,6 +262,7 @@ int launch_umma_gemm(int BN, const GemmParams& p, const CUtensorMap& ta, const C
     case 32: return launch_bn<32>(p, ta, tb, num_sms, st);
     case 48: return launch_bn<48>(p, ta, tb, num_sms, st);
     case 64: return launch_bn<64>(p, ta, tb, num_sms, st);
+    case 160: return launch_bn<160>(p, ta, tb, num_sms, st);
     case 192: return launch_bn<192>(p, ta, tb, num_sms, st);
     case 256: return launch_bn<256>(p, ta, tb, num_sms, st);
     default: set_error("launch_umma_gemm: unsupported N tile %d", BN); return 1;

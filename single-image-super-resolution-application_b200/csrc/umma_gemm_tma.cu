@@ -18,20 +18,21 @@ namespace {
 
 constexpr int kBoxBytes = 128 * 128;     // 128 rows x 128 B
 constexpr int kNBox = 6;                 // box buffers shared by the fp32 and bf16 streams
-constexpr int kMaxCols = 384;            // bias / gamma / beta staged in smem for every N tile (n_tiles * BN <= 384)
 constexpr int kEpiThreads = 256;         // 8 epilogue warps: two per TMEM lane quarter, each pair splits the columns
 
 template <int BN>
 struct TmaCfg {
-  static constexpr int kStages = (BN >= 192) ? 3 : 4;
+  static constexpr int kStages = (BN >= 160) ? 3 : 4;
   static constexpr int kABytes = 128 * 128;
   static constexpr int kBBytes = BN * 128;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int kPipeBytes = kStages * kStageBytes;
+  static constexpr int kMaxCols = (BN == 160) ? 960 : 384;   // bias / gamma / beta staged in smem for every N tile (n_tiles * BN <= kMaxCols)
   static constexpr int kParamBytes = 3 * kMaxCols * 4 + 2 * 2 * 128 * 8;     // bias|gamma|beta + LayerNorm partials
   static constexpr int kSmemBytes = kPipeBytes + kNBox * kBoxBytes + kParamBytes + 1024 + 512;
-  static constexpr int kGroups = BN / 64;       // 64-column groups per tile
+  static constexpr int kGroups = BN / 64;       // 64-column output groups per tile (BN = 160: the 128 gated columns of EPI_MSGATE)
+  static constexpr int kOutCols = kGroups * 64; // output columns produced per N tile
 };
 
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int c0, int c1) {
@@ -63,6 +64,8 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int w) {
 
 }  // namespace
 
+static_assert(TmaCfg<160>::kSmemBytes <= 232448 && TmaCfg<192>::kSmemBytes <= 232448 && TmaCfg<64>::kSmemBytes <= 232448, "smem budget");
+
 template <int BN>
 __global__ void __launch_bounds__(384, 1)
 umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
@@ -81,6 +84,7 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   const uint32_t box0 = smem_base + Cfg::kPipeBytes;
   uint8_t* box_ptr = smem_al + Cfg::kPipeBytes;
   float* s_bias = reinterpret_cast<float*>(box_ptr + kNBox * kBoxBytes);
+  constexpr int kMaxCols = Cfg::kMaxCols;
   float* s_gamma = s_bias + kMaxCols;
   float* s_beta = s_gamma + kMaxCols;
   float2* s_part = reinterpret_cast<float2*>(s_beta + kMaxCols);           // [2 tile parity][2 column halves][128 rows]
@@ -107,10 +111,10 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiThreads); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiThreads / 32); }
     for (int s = 0; s < kNBox; ++s) {
       mbar_init(in_bar(s), 1);
-      mbar_init(out_bar(s), s < nf ? 128 : 256);       // fp32 box: one column-half set writes it; bf16 box: both sets
+      mbar_init(out_bar(s), s < nf ? 4 : 8);           // warp-level arrivals; fp32 box: one column-half set (4 warps) writes it; bf16 box: both sets
     }
     fence_barrier_init();
   }
@@ -207,7 +211,7 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const TileCoord t = tile_coord(p, w);
         for (int j = 0; j < per_tile; ++j) {
-          const int col = t.n_tile * BN + width * j;
+          const int col = t.n_tile * Cfg::kOutCols + width * j;
           const int s = (int)(u_prep % (uint32_t)nb);
           const int b = first + s;
           if (u_prep >= (uint32_t)nb) { store_one(); tma_wait_read0(); }
@@ -242,6 +246,14 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       float mean = 0.f, rstd = 1.f;
+      float x1[32];
+      if (BN == 160 && p.epi == EPI_MSGATE) {
+        // MultipleSizeConvExtract gate (hit_sir_pro.py:83-92): tile columns [32k, 32k+32), k = 0..3 hold conv3/5/7/9 of 32 embedding
+        // channels, columns [128, 160) the 1x1 conv_x of the same channels; g_k = x_k * sigmoid(x_1 * x_k) + x_k
+        tmem_ld32(tacc + 128, x1);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) x1[i] += s_bias[n0 + 128 + i];
+      }
       if (p.epi == EPI_LN) {
         // one pass: sum and sum of squares of this thread's half of the row, combined with the partner warp
         float s = 0.f, ss = 0.f;
@@ -249,8 +261,7 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int g = 0; g < Cfg::kGroups; ++g) {
           const int c0 = 64 * g + 32 * hs;
           float v[32];
-          tmem_ld16(tacc + c0, v);
-          tmem_ld16(tacc + c0 + 16, v + 16);
+          tmem_ld32(tacc + c0, v);
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 bb = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + i);
@@ -275,14 +286,16 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int c0 = 64 * g + 32 * hs;               // tile-local first column of this thread's slice
         const int gc = n0 + c0;
         float v[32];
-        tmem_ld16(tacc + c0, v);
-        tmem_ld16(tacc + c0 + 16, v + 16);
+        tmem_ld32(tacc + c0, v);
 #pragma unroll
         for (int i = 0; i < 32; i += 4) {
           const float4 bb = *reinterpret_cast<const float4*>(s_bias + gc + i);
           v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
         }
-        if (p.epi == EPI_LN) {
+        if (BN == 160 && p.epi == EPI_MSGATE) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], sigmoidf_(x1[i] * v[i]), v[i]);
+        } else if (p.epi == EPI_LN) {
 #pragma unroll
           for (int i = 0; i < 32; i += 4) {
             const float4 gg = *reinterpret_cast<const float4*>(s_gamma + gc + i);      // zero beyond n_real -> pad columns become 0
@@ -322,7 +335,7 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             *ptr = o;
           }
           fence_proxy_async_smem();
-          mbar_arrive(out_bar(b));
+          mbar_arrive_warp(out_bar(b));
         }
         if (has_b16) {
           const uint32_t u = (uint32_t)it * (uint32_t)Cfg::kGroups + (uint32_t)g;
@@ -336,11 +349,11 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             *reinterpret_cast<uint4*>(hb + (((uint32_t)(4 * hs + ch) ^ rsw) << 4)) = o;
           }
           fence_proxy_async_smem();
-          mbar_arrive(out_bar(b));
+          mbar_arrive_warp(out_bar(b));
         }
       }
       tc_fence_before();
-      mbar_arrive(tempty_bar(as));
+      mbar_arrive_warp(tempty_bar(as));
     }
   }
   tc_fence_before();
@@ -362,7 +375,7 @@ static int launch_tma_bn(const GemmParams& p, const CUtensorMap* maps, int num_s
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   if (grid <= 0) return 0;
-  if (p.n_tiles * BN > kMaxCols) { set_error("launch_umma_gemm_tma: %d output columns exceed the staged-parameter limit %d", p.n_tiles * BN, kMaxCols); return 1; }
+  if (p.n_tiles * BN > Cfg::kMaxCols) { set_error("launch_umma_gemm_tma: %d output columns exceed the staged-parameter limit %d", p.n_tiles * BN, Cfg::kMaxCols); return 1; }
   umma_gemm_tma_kernel<BN><<<grid, 384, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
@@ -372,6 +385,7 @@ static int launch_tma_bn(const GemmParams& p, const CUtensorMap* maps, int num_s
 int launch_umma_gemm_tma(int BN, const GemmParams& p, const CUtensorMap* maps, int num_sms, cudaStream_t st) {
   switch (BN) {
     case 64: return launch_tma_bn<64>(p, maps, num_sms, st);
+    case 160: return launch_tma_bn<160>(p, maps, num_sms, st);
     case 192: return launch_tma_bn<192>(p, maps, num_sms, st);
     default: set_error("launch_umma_gemm_tma: unsupported N tile %d", BN); return 1;
   }

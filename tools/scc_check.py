@@ -94,7 +94,9 @@ def main():
         p = f"layers.0.residual_group.blocks.{j}.correlation."
         qkv = tap(f"block0.{j}.qkv", B * Hp * Wp * 180).view(B, Hp, Wp, 180)
         print(f"block0.{j} w={w} Hp={Hp} Wp={Wp}: qkv rel_l2 vs oracle = {rel_l2(qkv, taps[f'block0.{j}.qkv']):.3e}", flush=True)
-        dbg = tap(f"block0.{j}.sccdbg", 63488)
+        dbg = tap(f"block0.{j}.sccdbg", 63488 + 32)
+        tl = dbg[63488:63488 + 16]
+        print("    timeline (cycles since MMA-thread window start): " + " ".join(f"{int((v - tl[0]) % (1 << 24))}" for v in tl.tolist()), flush=True)
         G = dbg[:24576].view(128, 192)
         TPT = dbg[24576:36864].view(192, 64)
         corr = dbg[36864:49152].view(128, 96)
@@ -104,7 +106,8 @@ def main():
         tw = qkv[0, :w, :w, :].reshape(L, 180)
         T = torch.zeros(L, 192)
         T[:, perm] = tw
-        T[:, 15] = 1.0
+        for h in range(6):
+            T[:, 16 * h + 15] = 1.0
         G_ref = T[:, :128].t() @ T
         wsl = sd[p + "spatial_linear.weight"].view(r, r)
         bsl = sd[p + "spatial_linear.bias"].item()
@@ -125,7 +128,7 @@ def main():
         for h in range(6):
             Wk[16 * h:16 * h + 15, 16 * h:16 * h + 15] = 0.5 * w1
             Wk[16 * h:16 * h + 15, 96 + 16 * h:96 + 16 * h + 15] = 0.5 * w2
-            Wk[16 * h:16 * h + 15, 15] += 0.5 * (b1 + b2)
+            Wk[16 * h:16 * h + 15, 16 * h + 15] += 0.5 * (b1 + b2)
         corr_ref = (G_ref[:96] @ Wk.t()) / L
         KP_ref = TPT_raw.t() @ Wk.t()                 # [64, 96]
         KP_ref[:Lb, ~padrow] += bsl
