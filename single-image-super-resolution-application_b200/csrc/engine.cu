@@ -89,6 +89,7 @@ struct HitsirHandle {
   int device = 0;
   int num_sms = 148;
   bool simt = false;
+  bool scc_gram_only = false;     // HITSIR_SCC=gram: use the Gram-matrix kernel (scc_umma.cu) for every window size
   bool direct_epilogue = false;   // HITSIR_EPILOGUE=direct: per-row global stores instead of the TMA-staged epilogue
   std::vector<ParamSpec> params;
   std::map<std::string, int> index;
@@ -648,7 +649,10 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   {
     const bool want_dbg = h->tap.dst != nullptr && h->tap.name == tn + ".sccdbg";
     char cat[16]; snprintf(cat, sizeof(cat), "scc_w%d", w);
-    LAUNCH(cat, 1, launch_scc_umma(ws.T, g, bw.scc, ws.outsc, want_dbg ? ws.scc_dbg : nullptr, h->num_sms, f.st));
+    if (g.r == 1 && !want_dbg && !h->scc_gram_only)
+      LAUNCH(cat, 1, launch_scc_dense(ws.T, g, bw.scc, ws.outsc, h->num_sms, f.st));
+    else
+      LAUNCH(cat, 1, launch_scc_umma(ws.T, g, bw.scc, ws.outsc, want_dbg ? ws.scc_dbg : nullptr, h->num_sms, f.st));
   }
   TAP((tn + ".sccdbg").c_str(), ws.scc_dbg, 0, kSccDbgFloats, 1, kSccDbgFloats);
   TAPP((tn + ".scc").c_str(), ws.outsc, 1, kCp, f.N, kC);
@@ -853,6 +857,8 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
   if (cfg->in_chans == 3) { h->mean[0] = 0.485f; h->mean[1] = 0.456f; h->mean[2] = 0.4060f; }   // (:1128)
   const char* env = getenv("HITSIR_GEMM");
   h->simt = env && strcmp(env, "simt") == 0;
+  const char* env3 = getenv("HITSIR_SCC");
+  h->scc_gram_only = env3 && strcmp(env3, "gram") == 0;
   const char* env2 = getenv("HITSIR_EPILOGUE");
   h->direct_epilogue = env2 && strcmp(env2, "direct") == 0;
   build_param_list(h);

@@ -83,6 +83,8 @@ int launch_scc_images(const SccW& w, int win, int base, uint8_t* pool_img, uint8
 // dbg (optional): fp32 dump of window 0: G[128][192] | TPT[192][64] | corr[128][96] | KP[128][96] | Mblk[128][16]
 constexpr int kSccDbgFloats = 63488 + 32;   // + phase timeline (clock64) of one window
 int launch_scc_umma(const bf16* t, const SccGeom& g, const SccW& w, bf16* out, float* dbg, int num_sms, cudaStream_t st);
+// scc_dense.cu: windows of 4x4 / 8x8 tokens (pooling ratio 1), several windows per 128-token tile
+int launch_scc_dense(const bf16* t, const SccGeom& g, const SccW& w, bf16* out, int num_sms, cudaStream_t st);
 
 // ---- fusion (UnionAttention / Fusion, hit_sir_pro.py:104-162) -------------------------------------
 struct UaW {
