@@ -84,8 +84,8 @@ def category_flops(cat, B, H, W):
         "conv_layer": 2 * N * 9 * 180 * 180, "conv_after_body": 2 * N * 9 * 180 * 180, "conv_ua": 2 * N * 9 * 180 * 180,
         "conv_before_upsample": 2 * N * 9 * 180 * 64, "conv_up1": 2 * 4 * N * 9 * 64 * 64, "conv_up2": 2 * 16 * N * 9 * 64 * 64,
         "conv_hr": 2 * 16 * N * 9 * 64 * 64, "conv_last": 2 * 16 * N * 9 * 64 * 3,
-        "gemm_first_msgate": 2 * N * 3 * 180 * (9 + 25 + 49 + 81 + 1), "gemm_first_last_ln": 2 * N * 720 * 180,
-        "gemm_first_ln": 2 * N * 27 * 180,
+        "gemm_first_msgate": 2 * N * 3 * 180 * (9 + 25 + 49 + 81 + 1), "gemm_first_last": 2 * N * 720 * 180,
+        "gemm_first": 2 * N * 27 * 180,
     }
     if cat in table:
         return table[cat]
@@ -98,6 +98,35 @@ def category_flops(cat, B, H, W):
         # k-gen (2 x 15x15 per head), pooling Linear(r^2,1) on k and v, S-SC (q k^T, corr v), C-SC (q^T k, corr v^T)
         return Np * (2 * 2 * 6 * 15 * 15 + 2 * 2 * 90 + 2 * 2 * Lb * 90 + 2 * 2 * 90 * 90)
     return 0
+
+
+# algorithmic (compulsory, unpadded) HBM bytes of one launch of each bandwidth-bound category: DESIGN.md section 3
+def category_bytes(cat, B, H, W):
+    N = B * H * W
+    table = {
+        "dwconv5": N * (360 * 2 + 360 * 2),                       # bf16 hidden in, bf16 hidden out
+        "qkv_build": N * (180 * 4 + 180 * 2),                     # fp32 stream in, bf16 window tokens out
+        "sca_stats": N * 180 * 4,                                 # fp32 stream in (statistics out are negligible)
+        "gemm_proj_ln": N * (180 * 2 + 180 * 4 + 180 * 4 + 180 * 2),   # bf16 A, fp32 residual in, fp32 stream + bf16 shadow out
+        "gemm_fc2_ln": N * (360 * 2 + 180 * 4 + 180 * 4 + 180 * 2),
+        "gemm_fc1_gelu": N * (180 * 2 + 360 * 2),
+        "ln_rows": N * (180 * 4 + 180 * 4),
+        "fusion_combine": N * (5 * 180 * 4 + 180 * 2),
+        "upsample2": 0,
+    }
+    if cat in table:
+        return table[cat]
+    if cat.startswith("scc_w"):
+        return N * (180 * 2 + 180 * 2)                            # window tokens in (once), self-correlation out
+    return 0
+
+
+def measured_traffic(cat):
+    """DRAM bytes per launch of `cat` from the committed ncu capture (profiles/traffic.json), or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        return json.load(open(path)).get(cat)
+    return None
 
 
 def run_ours(args):
@@ -175,10 +204,30 @@ def run_ours(args):
     # dominant kernel category of the step
     cat, (cat_ms, cat_n) = max(prof.items(), key=lambda kv: kv[1][0])
     fl = category_flops(cat, B, H, W)
-    achieved = fl / (cat_ms / cat_n / 1e3) / 1e12 if fl else None
+    by = category_bytes(cat, B, H, W)
+    t_launch = cat_ms / cat_n / 1e3
+    tflops = fl / t_launch / 1e12 if fl else None
+    gbs = by / t_launch / 1e9 if by else None
+    # the roofline that binds the dominant kernel: whichever of its two fractions is larger
+    f_t = tflops / pk["bf16_sustained"] if tflops else 0.0
+    f_h = gbs / pk["hbm"] if gbs else 0.0
+    if f_h >= f_t and gbs:
+        roof = {"bound": "hbm", "kernel": cat, "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(f_h, 4),
+                "algorithmic_bytes_per_launch": by}
+    else:
+        roof = {"bound": "tensor", "kernel": cat, "achieved": round(tflops, 2) if tflops else None, "peak": pk["bf16_sustained"],
+                "unit": "TFLOP/s", "frac": round(f_t, 4) if tflops else None, "algorithmic_flops_per_launch": fl}
+    tr = measured_traffic(cat)
+    roof["traffic"] = tr.get("bytes_per_launch") if isinstance(tr, dict) else tr
+    if isinstance(tr, dict):
+        roof["traffic_note"] = tr.get("note")
     whole = GFLOP_PER_IMAGE.get(args.workload, 0) * B / (ms_step / 1e3) / 1e3
+    roof.update({"peak_source": pk["src"] + (" (sustained, kernel timed inside a long step)" if roof["bound"] == "tensor" else " (copy bandwidth)"),
+                 "kernel_share_of_step": round(cat_ms / ms_total, 3), "launch_ms": round(t_launch * 1e3, 4),
+                 "whole_forward_tflops": round(whole, 1), "whole_forward_frac": round(whole / pk["bf16_sustained"], 4)})
     breakdown = {k: {"ms_per_step": round(v[0] / args.steps, 3), "launches_per_step": v[1] // args.steps,
-                     "tflops": round(category_flops(k, B, H, W) / (v[0] / v[1] / 1e3) / 1e12, 1) if category_flops(k, B, H, W) else None}
+                     "tflops": round(category_flops(k, B, H, W) / (v[0] / v[1] / 1e3) / 1e12, 1) if category_flops(k, B, H, W) else None,
+                     "gbs": round(category_bytes(k, B, H, W) / (v[0] / v[1] / 1e3) / 1e9, 0) if category_bytes(k, B, H, W) else None}
                  for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
     line = {
         "metric": "HiT-SIR-pro x4 output megapixels/s", "value": round(value, 3), "unit": "MP/s", "n_gpus": world,
@@ -191,11 +240,7 @@ def run_ours(args):
                 "d2h_bytes_per_step": B * 3 * H * W * scale * scale * 4, "ms_per_step": round(e2e_ms, 3)},
         "gpu_launches": launches_per_step * args.steps,
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": cat, "achieved": round(achieved, 2) if achieved else None, "peak": pk["bf16_sustained"],
-                     "unit": "TFLOP/s", "frac": round(achieved / pk["bf16_sustained"], 4) if achieved else None, "traffic": None,
-                     "peak_source": pk["src"] + " (sustained, kernel timed inside a long step)",
-                     "kernel_share_of_step": round(cat_ms / ms_total, 3),
-                     "whole_forward_tflops": round(whole, 1), "whole_forward_frac": round(whole / pk["bf16_sustained"], 4)},
+        "roofline": roof,
         "breakdown": breakdown,
     }
     if rank == 0:

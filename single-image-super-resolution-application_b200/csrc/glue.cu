@@ -215,17 +215,30 @@ __global__ void __launch_bounds__(256) sca_stats_kernel(const float* __restrict_
   float asum[6], amax[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) { asum[i] = 0.f; amax[i] = -INFINITY; }
-  for (int pp = p0 + warp; pp < p1; pp += 8) {
-    const int yp = pp / g.Wp, xp = pp - yp * g.Wp;
-    const float* r = x + (((long long)b * g.H + reflect_src(yp, g.H)) * g.W + reflect_src(xp, g.W)) * kC;
-    float s = 0.f, m = -INFINITY;
+  // four pixels per warp iteration: 24 independent loads in flight before the shuffle reductions
+  for (int pp0 = p0 + warp * 4; pp0 < p1; pp0 += 32) {
+    float v[4][6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-      const int c = lane + 32 * i;
-      if (c < kC) { const float v = r[c]; s += v; m = fmaxf(m, v); asum[i] += v; amax[i] = fmaxf(amax[i], v); }
+    for (int u = 0; u < 4; ++u) {
+      const int pp = min(pp0 + u, p1 - 1);
+      const int yp = pp / g.Wp, xp = pp - yp * g.Wp;
+      const float* r = x + (((long long)b * g.H + reflect_src(yp, g.H)) * g.W + reflect_src(xp, g.W)) * kC;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) { const int c = lane + 32 * i; v[u][i] = c < kC ? r[c] : 0.f; }
     }
-    s = warp_sum(s); m = warp_max(m);
-    if (lane == 0) { cavg[(long long)b * npix + pp] = s / (float)kC; cmax[(long long)b * npix + pp] = m; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pp = pp0 + u;
+      if (pp >= p1) break;
+      float s = 0.f, m = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int c = lane + 32 * i;
+        if (c < kC) { s += v[u][i]; m = fmaxf(m, v[u][i]); asum[i] += v[u][i]; amax[i] = fmaxf(amax[i], v[u][i]); }
+      }
+      s = warp_sum(s); m = warp_max(m);
+      if (lane == 0) { cavg[(long long)b * npix + pp] = s / (float)kC; cmax[(long long)b * npix + pp] = m; }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 6; ++i) { s_sum[warp][lane + 32 * i] = asum[i]; s_max[warp][lane + 32 * i] = amax[i]; }
@@ -290,7 +303,7 @@ __global__ void qkv_build_kernel(const float* __restrict__ x, PadGeom g, bf16* _
 // memory; per pixel a thread does 18 packed FMAs, one 8-byte token load and one 4-byte bf16x2 store, so a warp
 // reads/writes whole contiguous token rows.
 constexpr int kQkvRun = 64;
-__global__ void __launch_bounds__(96) qkv_casa_kernel(const float* __restrict__ x, PadGeom g, const float* __restrict__ cavg,
+__global__ void __launch_bounds__(96, 10) qkv_casa_kernel(const float* __restrict__ x, PadGeom g, const float* __restrict__ cavg,
                                                       const float* __restrict__ cmax, const float* __restrict__ s1, const float* __restrict__ s2,
                                                       CasaW w, bf16* __restrict__ t, int runs) {
   __shared__ float sa[3][kQkvRun + 2], sm[3][kQkvRun + 2];
@@ -328,7 +341,7 @@ __global__ void __launch_bounds__(96) qkv_casa_kernel(const float* __restrict__ 
   float a0[3], a1c[3], m0[3], m1c[3];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) { a0[ky] = sa[ky][0]; a1c[ky] = sa[ky][1]; m0[ky] = sm[ky][0]; m1c[ky] = sm[ky][1]; }
-  constexpr int kBatch = 8;
+  constexpr int kBatch = 4;
   for (int i0 = 0; i0 < n; i0 += kBatch) {
     float2 xv[kBatch];
 #pragma unroll
