@@ -671,7 +671,9 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   // fc2 + norm2 + residual (:704)
   base_params(p, bw.fc2);
   p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g2; p.beta = bw.b2; p.res = xout; p.ldr = kC;
-  p.out_f32 = xout; p.ldf = kC; p.out_bf16 = ws.xb0; p.ldb = kCp;
+  p.out_f32 = xout; p.ldf = kC;
+  // the bf16 shadow of the block output is only consumed by the RHTB conv after the last block of a layer (:934)
+  if (j == c.depths[i] - 1) { p.out_bf16 = ws.xb0; p.ldb = kCp; }
   RUN(linear(f, "gemm_fc2_ln", bw.fc2, ws.H2, f.N, p));
   TAP(tn.c_str(), xout, 0, kC, f.N, kC);
   return 0;

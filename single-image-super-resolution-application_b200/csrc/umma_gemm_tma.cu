@@ -18,7 +18,8 @@ namespace {
 
 constexpr int kBoxBytes = 128 * 128;     // 128 rows x 128 B
 constexpr int kNBox = 6;                 // box buffers shared by the fp32 and bf16 streams
-constexpr int kEpiThreads = 256;         // 8 epilogue warps: two per TMEM lane quarter, each pair splits the columns
+// Epilogue warps: EQ per TMEM lane quarter (2 or 4), each handles a 64/EQ-column slice of every 64-column group.  EQ = 4 (16 warps)
+// hides the TMEM-load / math / store latency chain of the activation epilogues; the LayerNorm epilogues are HBM-bound and keep EQ = 2.
 
 template <int BN>
 struct TmaCfg {
@@ -44,8 +45,10 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }   // all but the newest group
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }   // the 256 epilogue threads only
+template <int N>
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }   // the epilogue threads only
 
 struct TileCoord {
   int m_tile, n_tile, b, y0, x0;
@@ -66,8 +69,8 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmParams& p, int w) {
 
 static_assert(TmaCfg<160>::kSmemBytes <= 232448 && TmaCfg<192>::kSmemBytes <= 232448 && TmaCfg<64>::kSmemBytes <= 232448, "smem budget");
 
-template <int BN>
-__global__ void __launch_bounds__(384, 1)
+template <int BN, int EQ>
+__global__ void __launch_bounds__(128 + 128 * EQ, 1)
 umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                      const __grid_constant__ CUtensorMap tmap_f, const __grid_constant__ CUtensorMap tmap_h,
                      const __grid_constant__ CUtensorMap tmap_r, const GemmParams p) {
@@ -111,10 +114,10 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), kEpiThreads / 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * EQ); }
     for (int s = 0; s < kNBox; ++s) {
       mbar_init(in_bar(s), 1);
-      mbar_init(out_bar(s), s < nf ? 4 : 8);           // warp-level arrivals; fp32 box: one column-half set (4 warps) writes it; bf16 box: both sets
+      mbar_init(out_bar(s), s < nf ? 2 * EQ : 4 * EQ);   // warp-level arrivals; fp32 box (32 columns): half of the slices; bf16 box (64): all
     }
     fence_barrier_init();
   }
@@ -214,7 +217,14 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           const int col = t.n_tile * Cfg::kOutCols + width * j;
           const int s = (int)(u_prep % (uint32_t)nb);
           const int b = first + s;
-          if (u_prep >= (uint32_t)nb) { store_one(); tma_wait_read0(); }
+          if (u_prep >= (uint32_t)nb) {
+            // box s was last used by store #(u_prep - nb).  Bulk groups retire in order, so once the stores through #(u_prep - nb + 1)
+            // are issued, "at most one group pending" proves that store has finished reading shared memory -- without waiting for the
+            // newest store (waiting for group 0 here exposed one full store latency per box: ~6k cycles per fc1 tile).
+            const uint32_t need = u_prep - (uint32_t)nb + 2u;
+            while (u_store < need && u_store < u_prep) store_one();
+            tma_wait_read1();
+          }
           c0s[s] = col;
           if (p.conv) { r0s[s] = t.x0; r1s[s] = t.y0; r2s[s] = t.b; } else { r0s[s] = t.m_tile * 128; r1s[s] = 0; r2s[s] = 0; }
           if (f_lane && has_res && col < ncol_limit) {
@@ -233,10 +243,14 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   } else if (warp >= 4) {
     // ===================== epilogue compute (8 warps) =====================
     const int q = warp & 3;                            // TMEM lane quarter of this warp
-    const int hs = (warp - 4) >> 2;                    // column half handled by this warp: slices 64g + 32*hs
+    constexpr int SW = 64 / EQ;                        // slice width (columns) of one thread
+    const int hs = (warp - 4) >> 2;                    // slice handled by this warp: columns 64g + SW*hs of every 64-column group g
     const int r = q * 32 + lane;
     const uint32_t rsw = (uint32_t)(r & 7);
     uint8_t* row_ptr = box_ptr + r * 128;              // this thread's row inside box 0
+    auto ld_slice = [&](uint32_t taddr, float* v) {
+      if constexpr (SW == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+    };
     int it = 0;
     for (int w = blockIdx.x; w < total; w += gridDim.x, ++it) {
       const int n_tile = w % p.n_tiles;
@@ -246,24 +260,25 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
       float mean = 0.f, rstd = 1.f;
-      float x1[32];
+      float x1[SW];
       if (BN == 160 && p.epi == EPI_MSGATE) {
         // MultipleSizeConvExtract gate (hit_sir_pro.py:83-92): tile columns [32k, 32k+32), k = 0..3 hold conv3/5/7/9 of 32 embedding
         // channels, columns [128, 160) the 1x1 conv_x of the same channels; g_k = x_k * sigmoid(x_1 * x_k) + x_k
-        tmem_ld32(tacc + 128, x1);
+        const int ci0 = (SW * hs) & 31;
+        ld_slice(tacc + 128 + ci0, x1);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) x1[i] += s_bias[n0 + 128 + i];
+        for (int i = 0; i < SW; ++i) x1[i] += s_bias[n0 + 128 + ci0 + i];
       }
       if (p.epi == EPI_LN) {
-        // one pass: sum and sum of squares of this thread's half of the row, combined with the partner warp
+        // one pass: sum and sum of squares of this thread's slices of the row, combined with the partner warps
         float s = 0.f, ss = 0.f;
 #pragma unroll 1
         for (int g = 0; g < Cfg::kGroups; ++g) {
-          const int c0 = 64 * g + 32 * hs;
-          float v[32];
-          tmem_ld32(tacc + c0, v);
+          const int c0 = 64 * g + SW * hs;
+          float v[SW];
+          ld_slice(tacc + c0, v);
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < SW; i += 4) {
             const float4 bb = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + i);
             const float t0 = v[i] + bb.x, t1 = v[i + 1] + bb.y, t2 = v[i + 2] + bb.z, t3 = v[i + 3] + bb.w;
             if (c0 + i < p.n_real) { s += t0; ss = fmaf(t0, t0, ss); }
@@ -272,32 +287,36 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             if (c0 + i + 3 < p.n_real) { s += t3; ss = fmaf(t3, t3, ss); }
           }
         }
-        float2* part = s_part + (it & 1) * 256;
+        float2* part = s_part + (it & 1) * (EQ * 128);
         part[hs * 128 + r] = make_float2(s, ss);
-        epi_bar_sync();
-        const float2 o = part[(hs ^ 1) * 128 + r];
+        epi_bar_sync<128 * EQ>();
+#pragma unroll
+        for (int o = 1; o < EQ; ++o) {
+          const float2 t = part[((hs + o) % EQ) * 128 + r];
+          s += t.x; ss += t.y;
+        }
         const float inv_n = 1.0f / (float)p.n_real;
-        mean = (s + o.x) * inv_n;
-        const float var = fmaxf((ss + o.y) * inv_n - mean * mean, 0.f);
+        mean = s * inv_n;
+        const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
         rstd = rsqrtf(var + 1e-5f);
       }
 #pragma unroll 1
       for (int g = 0; g < Cfg::kGroups; ++g) {
-        const int c0 = 64 * g + 32 * hs;               // tile-local first column of this thread's slice
+        const int c0 = 64 * g + SW * hs;               // tile-local first column of this thread's slice
         const int gc = n0 + c0;
-        float v[32];
-        tmem_ld32(tacc + c0, v);
+        float v[SW];
+        ld_slice(tacc + c0, v);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
+        for (int i = 0; i < SW; i += 4) {
           const float4 bb = *reinterpret_cast<const float4*>(s_bias + gc + i);
           v[i] += bb.x; v[i + 1] += bb.y; v[i + 2] += bb.z; v[i + 3] += bb.w;
         }
         if (BN == 160 && p.epi == EPI_MSGATE) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], sigmoidf_(x1[i] * v[i]), v[i]);
+          for (int i = 0; i < SW; ++i) v[i] = fmaf(v[i], sigmoidf_(x1[i] * v[i]), v[i]);
         } else if (p.epi == EPI_LN) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 4) {
+          for (int i = 0; i < SW; i += 4) {
             const float4 gg = *reinterpret_cast<const float4*>(s_gamma + gc + i);      // zero beyond n_real -> pad columns become 0
             const float4 be = *reinterpret_cast<const float4*>(s_beta + gc + i);
             v[i] = fmaf((v[i] - mean) * rstd, gg.x, be.x);
@@ -308,24 +327,26 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         } else {
           if (p.act == ACT_GELU) {
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) { const float2 g = gelu2(make_float2(v[i], v[i + 1])); v[i] = g.x; v[i + 1] = g.y; }
+            for (int i = 0; i < SW; i += 2) { const float2 gl = gelu2(make_float2(v[i], v[i + 1])); v[i] = gl.x; v[i + 1] = gl.y; }
           } else if (p.act == ACT_LRELU) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = lrelu(v[i], p.slope);
+            for (int i = 0; i < SW; ++i) v[i] = lrelu(v[i], p.slope);
           }
-          if (gc + 32 > p.n_real) {
+          if (gc + SW > p.n_real) {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = (gc + i < p.n_real) ? v[i] : 0.f;
+            for (int i = 0; i < SW; ++i) v[i] = (gc + i < p.n_real) ? v[i] : 0.f;
           }
         }
         if (has_f32) {
-          const uint32_t u = (uint32_t)it * (uint32_t)(2 * Cfg::kGroups) + (uint32_t)(2 * g + hs);
+          // fp32 boxes hold 32 columns: box index 2g + (c0 % 64) / 32, this slice covers SW/4 of its 8 chunks
+          const uint32_t u = (uint32_t)it * (uint32_t)(2 * Cfg::kGroups) + (uint32_t)(2 * g + ((SW * hs) >> 5));
           const int b = (int)(u % (uint32_t)nf);
           mbar_wait(in_bar(b), (u / (uint32_t)nf) & 1u);
           uint8_t* fb = row_ptr + b * kBoxBytes;
+          const uint32_t ch0 = (uint32_t)(((SW * hs) & 31) >> 2);
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) {
-            float4* ptr = reinterpret_cast<float4*>(fb + (((uint32_t)ch ^ rsw) << 4));
+          for (int ch = 0; ch < SW / 4; ++ch) {
+            float4* ptr = reinterpret_cast<float4*>(fb + (((ch0 + (uint32_t)ch) ^ rsw) << 4));
             float4 o = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
             if (has_res) {
               const float4 rr = *ptr;
@@ -343,10 +364,10 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           mbar_wait(in_bar(b), (u / (uint32_t)nh) & 1u);
           uint8_t* hb = row_ptr + b * kBoxBytes;
 #pragma unroll
-          for (int ch = 0; ch < 4; ++ch) {
+          for (int ch = 0; ch < SW / 8; ++ch) {
             uint4 o = make_uint4(pack_bf16x2(v[8 * ch], v[8 * ch + 1]), pack_bf16x2(v[8 * ch + 2], v[8 * ch + 3]),
                                  pack_bf16x2(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16x2(v[8 * ch + 6], v[8 * ch + 7]));
-            *reinterpret_cast<uint4*>(hb + (((uint32_t)(4 * hs + ch) ^ rsw) << 4)) = o;
+            *reinterpret_cast<uint4*>(hb + (((uint32_t)((SW / 8) * hs + ch) ^ rsw) << 4)) = o;
           }
           fence_proxy_async_smem();
           mbar_arrive_warp(out_bar(b));
@@ -364,29 +385,30 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   }
 }
 
-template <int BN>
+template <int BN, int EQ>
 static int launch_tma_bn(const GemmParams& p, const CUtensorMap* maps, int num_sms, cudaStream_t st) {
   using Cfg = TmaCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    HITSIR_CHECK(cudaFuncSetAttribute(umma_gemm_tma_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    HITSIR_CHECK(cudaFuncSetAttribute(umma_gemm_tma_kernel<BN, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   if (grid <= 0) return 0;
   if (p.n_tiles * BN > Cfg::kMaxCols) { set_error("launch_umma_gemm_tma: %d output columns exceed the staged-parameter limit %d", p.n_tiles * BN, Cfg::kMaxCols); return 1; }
-  umma_gemm_tma_kernel<BN><<<grid, 384, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  umma_gemm_tma_kernel<BN, EQ><<<grid, 128 + 128 * EQ, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
 
 // maps: {A, B, out_f32, out_bf16, residual}; unused maps may be copies of any valid map
 int launch_umma_gemm_tma(int BN, const GemmParams& p, const CUtensorMap* maps, int num_sms, cudaStream_t st) {
+  const bool wide = p.epi != EPI_LN;      // 16 epilogue warps for the activation / gate / plain-store epilogues
   switch (BN) {
-    case 64: return launch_tma_bn<64>(p, maps, num_sms, st);
-    case 160: return launch_tma_bn<160>(p, maps, num_sms, st);
-    case 192: return launch_tma_bn<192>(p, maps, num_sms, st);
+    case 64: return launch_tma_bn<64, 2>(p, maps, num_sms, st);     // 64-column tiles: the 8-warp epilogue is already hidden under the 9-tap mainloop
+    case 160: return launch_tma_bn<160, 4>(p, maps, num_sms, st);
+    case 192: return wide ? launch_tma_bn<192, 4>(p, maps, num_sms, st) : launch_tma_bn<192, 2>(p, maps, num_sms, st);
     default: set_error("launch_umma_gemm_tma: unsupported N tile %d", BN); return 1;
   }
 }
