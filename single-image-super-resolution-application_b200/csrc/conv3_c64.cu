@@ -1,0 +1,229 @@
+// 3x3 convolution over a 64-channel NHWC bf16 map (the HR stage of the 'nearest+conv' / 'pixelshuffle' upsamplers:
+// conv_up1, conv_up2, conv_hr 64 -> 64 with LeakyReLU, conv_last 64 -> in_chans; /root/reference/models/hit_sir_pro.py:1326-1334)
+// as an implicit GEMM on tcgen05, specialised for Cin = 64:
+//   * the whole filter bank (9 taps x BN x 64 bf16 = 72 KB for BN = 64) stays resident in shared memory for the life of the
+//     persistent CTA -- the generic kernel re-fetched 8 KB of weights per tap per tile from L2;
+//   * one TMA box per horizontal tap offset kx covers all three vertical taps: a (8+2) x 16 pixel box, whose rows ky*16 ..
+//     ky*16+127 are the A operand of tap (ky, kx) (descriptor start + ky * 2 KB, still 1024-byte aligned).  Every input pixel
+//     is therefore fetched 3.75x per tile instead of 9x; the generic kernel was bound by L2->SM traffic (~10 TB/s), not by HBM.
+// Out-of-image taps are TMA out-of-bounds zero fill (= the conv's zero padding).
+// BN = 64: bias + LeakyReLU -> bf16 NHWC via a swizzled box and TMA store.  BN = 16: conv_last, n_real <= 4 output channels,
+// de-normalised (x / img_range + mean, :1342) and written straight to the NCHW fp32 image.
+#include "gemm.cuh"
+
+namespace hitsir {
+
+namespace {
+
+constexpr int kATile = 160 * 128;          // (8 + 2) rows x 16 pixels x 64 ch bf16
+constexpr int kAStages = 4;
+constexpr int kBoxBytes = 128 * 128;
+constexpr int kNBox = 3;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = 9 * BN * 128;                      // resident filter bank
+  static constexpr int kOffA = (kBBytes + 1023) / 1024 * 1024;
+  static constexpr int kOffBox = kOffA + kAStages * kATile;
+  static constexpr int kOffBias = kOffBox + (BN == 64 ? kNBox * kBoxBytes : 0);
+  static constexpr int kOffBars = kOffBias + 64 * 4;
+  static constexpr int kSmemBytes = kOffBars + 32 * 8 + 16 + 1024;
+  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : 128;
+};
+
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+template <int BN>
+__global__ void __launch_bounds__(384, 1)
+conv3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o,
+                 const GemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sb - smem_u32(smem_raw));
+  float* s_bias = reinterpret_cast<float*>(sp + C::kOffBias);
+  const uint32_t bar0 = sb + C::kOffBars;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kAStages + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kAStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kAStages + 2 + s); };
+  auto box_free = [&](int s) { return bar0 + 8u * (2 * kAStages + 4 + s); };
+  auto box_ready = [&](int s) { return bar0 + 8u * (2 * kAStages + 4 + kNBox + s); };
+  const uint32_t b_full = bar0 + 8u * (2 * kAStages + 4 + 2 * kNBox);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sp + C::kOffBars + 32 * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.m_tiles;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); if (BN == 64) tma_prefetch_desc(&tmap_o); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kAStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+    for (int s = 0; s < kNBox; ++s) { mbar_init(box_free(s), 1); mbar_init(box_ready(s), 8); }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), C::kTmemCols); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_bias[i] = i < BN ? p.bias[i] : 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_xyb = [&](int t, int* x0, int* y0, int* b) {
+    const int tx = t % p.tiles_x; const int t2 = t / p.tiles_x;
+    *x0 = tx * 16; *y0 = (t2 % p.tiles_y) * 8; *b = t2 / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== producer: filter bank once, then one halo box per (tile, kx) =====================
+      mbar_expect_tx(b_full, (uint32_t)C::kBBytes);
+      for (int tap = 0; tap < 9; ++tap) tma_load_2d(sb + tap * BN * 128, &tmap_b, b_full, tap * 64, 0);
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        for (int kx = 0; kx < 3; ++kx, ++cnt) {
+          const int s = (int)(cnt % kAStages);
+          mbar_wait(empty_bar(s), ((cnt / kAStages) & 1u) ^ 1u);
+          mbar_expect_tx(full_bar(s), kATile);
+          tma_load_4d(sb + C::kOffA + s * kATile, &tmap_a, full_bar(s), 0, x0 + kx - 1, y0 - 1, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer: 3 (kx) x 3 (ky) x 4 (k-steps) per tile =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      mbar_wait(b_full, 0u);
+      uint32_t cnt = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kx = 0; kx < 3; ++kx, ++cnt) {
+          const int s = (int)(cnt % kAStages);
+          mbar_wait(full_bar(s), (cnt / kAStages) & 1u);
+          tc_fence_after();
+          const uint32_t sa = sb + C::kOffA + s * kATile;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint64_t adesc = umma_desc_sw128(sa + ky * 2048);
+            const uint64_t bdesc = umma_desc_sw128(sb + (ky * 3 + kx) * BN * 128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kx | ky | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else if (warp == 3) {
+    if (BN == 64 && lane == 0) {
+      // ===================== TMA store of finished boxes =====================
+      uint32_t u = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++u) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        const int s = (int)(u % kNBox);
+        mbar_wait(box_ready(s), (u / kNBox) & 1u);
+        tma_store_4d(&tmap_o, sb + C::kOffBox + s * kBoxBytes, 0, x0, y0, b);
+        tma_commit();
+        tma_wait_read1();                                  // groups retire in order: the previous box is free again
+        if (u >= 1) mbar_arrive(box_free((int)((u - 1) % kNBox)));
+      }
+      tma_wait_all0();
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 8 warps, two per TMEM lane quarter =====================
+    const int q = warp & 3, hs = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    int it = 0;
+    uint32_t u = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it, ++u) {
+      const int as = it & 1;
+      mbar_wait(tfull_bar(as), ((uint32_t)(it >> 1)) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      if constexpr (BN == 64) {
+        float v[32];
+        tmem_ld32(tacc + 32 * hs, v);
+        tc_fence_before();
+        mbar_arrive_warp(tempty_bar(as));
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const float x = v[i] + s_bias[32 * hs + i]; v[i] = p.act == ACT_LRELU ? lrelu(x, p.slope) : x; }
+        const int s = (int)(u % kNBox);
+        if (u >= (uint32_t)kNBox) mbar_wait(box_free(s), ((u / kNBox) - 1u) & 1u);
+        uint8_t* row = sp + C::kOffBox + s * kBoxBytes + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint4 o = make_uint4(pack_bf16x2(v[8 * ch], v[8 * ch + 1]), pack_bf16x2(v[8 * ch + 2], v[8 * ch + 3]),
+                                     pack_bf16x2(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16x2(v[8 * ch + 6], v[8 * ch + 7]));
+          *reinterpret_cast<uint4*>(row + (((uint32_t)(4 * hs + ch) ^ (uint32_t)(r & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive_warp(box_ready(s));
+      } else {
+        // conv_last: columns [0, n_real) -> NCHW fp32 image, x / img_range + mean (:1342); lanes = 16 consecutive x per image row
+        float v[16];
+        if (hs == 0) tmem_ld16(tacc, v);
+        tc_fence_before();
+        mbar_arrive_warp(tempty_bar(as));
+        if (hs == 0) {
+          int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+          const int y = y0 + (r >> 4), x = x0 + (r & 15);
+          if (y < p.H && x < p.W) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < p.n_real) p.out_f32[(((long long)b * p.shuf_c + c) * p.H + y) * p.W + x] = (v[c] + s_bias[c]) * p.out_scale + p.mean[c];
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+template <int BN>
+int launch_bn(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, int num_sms, cudaStream_t st) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    HITSIR_CHECK(cudaFuncSetAttribute(conv3_c64_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    configured = true;
+  }
+  const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
+  if (grid <= 0) return 0;
+  conv3_c64_kernel<BN><<<grid, 384, C::kSmemBytes, st>>>(ta, tb, to, p);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// A: NHWC bf16 [B,H,W,64]; tb: packed weights [BN][576] with a {64, BN} box; BN = 64 -> out_bf16 [B,H,W,64], BN = 16 -> out_f32 NCHW
+int launch_conv3_c64(int BN, const GemmParams& p, const bf16* A, const CUtensorMap& tb, int num_sms, cudaStream_t st) {
+  CUtensorMap ta, to;
+  if (make_tmap_nhwc(&ta, A, p.B, p.H, p.W, 64, 64, 16, 10)) return 1;
+  to = ta;
+  if (BN == 64) {
+    if (make_tmap_nhwc(&to, p.out_bf16, p.B, p.H, p.W, 64, 64, 16, 8)) return 1;
+    return launch_bn<64>(p, ta, tb, to, num_sms, st);
+  }
+  if (BN == 16) return launch_bn<16>(p, ta, tb, to, num_sms, st);
+  set_error("launch_conv3_c64: unsupported N tile %d", BN);
+  return 1;
+}
+
+}  // namespace hitsir

@@ -610,6 +610,14 @@ int conv3(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, 
   p.cblocks = Cpad / 64;
   p.A = A; p.lda = Cpad;
   if (w.K != 9 * Cpad) { set_error("conv3: packed K %d != 9*%d", w.K, Cpad); return 1; }
+  // 64-channel inputs (HR stage): resident filter bank + kx-shared halo boxes (conv3_c64.cu)
+  if (!f.h->simt && !f.h->direct_epilogue && Cpad == 64 && p.res == nullptr && p.out2_f32 == nullptr &&
+      ((w.BN == 64 && p.epi == EPI_STORE && p.out_bf16 != nullptr && p.out_f32 == nullptr && p.ldb == 64) ||
+       (w.BN == 16 && p.epi == EPI_SHUFFLE_NCHW && p.ps == 1 && p.n_real <= 4))) {
+    ProfScope ps(f.h, f.st, cat);
+    f.h->launches++;
+    return launch_conv3_c64(w.BN, p, A, w.tm, f.h->num_sms, f.st);
+  }
   CUtensorMap maps[5];
   const bool tma = tma_epilogue(f.h, w, p);
   if (!f.h->simt) {
