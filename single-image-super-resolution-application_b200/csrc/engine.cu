@@ -89,6 +89,7 @@ struct HitsirHandle {
   int device = 0;
   int num_sms = 148;
   bool simt = false;
+  bool ffn_unfused = false;       // HITSIR_FFN=unfused: separate dwconv5 and fc2 kernels for every block
   bool scc_gram_only = false;     // HITSIR_SCC=gram: use the Gram-matrix kernel (scc_umma.cu) for every window size
   bool direct_epilogue = false;   // HITSIR_EPILOGUE=direct: per-row global stores instead of the TMA-staged epilogue
   std::vector<ParamSpec> params;
@@ -383,7 +384,9 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
       if (make_gemm_w(h, &bw.proj, s + ".proj", C, C, 1, st, 1)) return 1;
       if (make_gemm_w(h, &bw.fc1, p + ".mlp.fc1", kHid, C, 1, st)) return 1;
       if (make_gemm_w(h, &bw.fc2, p + ".mlp.fc2", C, kHid, 1, st)) return 1;
-      if (dev_alloc(h, &bw.dw_w, 25 * kHidp) || dev_alloc(h, &bw.dw_b, kHidp)) return 1;
+      // [26][384] fp32: 25 tap rows + the bias as row 25 (one TMA box per 64-channel slice in ffn_tail.cu)
+      if (dev_alloc(h, &bw.dw_w, 26 * kHidp)) return 1;
+      bw.dw_b = bw.dw_w + 25 * kHidp;
       if (launch_pack_tapmajor(P(h, p + ".mlp.dwconv.depthwise_conv.0.weight"), bw.dw_w, kHid, 25, kHidp, st)) return 1;
       if (launch_pack_tapmajor(P(h, p + ".mlp.dwconv.depthwise_conv.0.bias"), bw.dw_b, kHid, 1, kHidp, st)) return 1;
     }
@@ -675,14 +678,19 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   base_params(p, bw.fc1);
   p.epi = EPI_STORE; p.act = ACT_GELU; p.n_real = kHid; p.out_bf16 = ws.H1; p.ldb = kHidp;
   RUN(linear(f, "gemm_fc1_gelu", bw.fc1, ws.xb0, f.N, p));
-  LAUNCH("dwconv5", 1, launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, h->num_sms, f.st));
-  // fc2 + norm2 + residual (:704)
-  base_params(p, bw.fc2);
-  p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g2; p.beta = bw.b2; p.res = xout; p.ldr = kC;
-  p.out_f32 = xout; p.ldf = kC;
-  // the bf16 shadow of the block output is only consumed by the RHTB conv after the last block of a layer (:934)
-  if (j == c.depths[i] - 1) { p.out_bf16 = ws.xb0; p.ldb = kCp; }
-  RUN(linear(f, "gemm_fc2_ln", bw.fc2, ws.H2, f.N, p));
+  const bool need_shadow = (j == c.depths[i] - 1);      // the RHTB conv after the last block reads a bf16 shadow of the stream (:934)
+  if (!h->simt && !h->direct_epilogue && !h->ffn_unfused && !need_shadow) {
+    // dwconv5 + GELU + input, fc2, norm2 and the residual add in one kernel: the hidden map h2 never reaches HBM
+    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_w, bw.fc2.tm, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, h->num_sms, f.st));
+  } else {
+    LAUNCH("dwconv5", 1, launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, h->num_sms, f.st));
+    // fc2 + norm2 + residual (:704)
+    base_params(p, bw.fc2);
+    p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g2; p.beta = bw.b2; p.res = xout; p.ldr = kC;
+    p.out_f32 = xout; p.ldf = kC;
+    if (need_shadow) { p.out_bf16 = ws.xb0; p.ldb = kCp; }
+    RUN(linear(f, "gemm_fc2_ln", bw.fc2, ws.H2, f.N, p));
+  }
   TAP(tn.c_str(), xout, 0, kC, f.N, kC);
   return 0;
 }
@@ -867,6 +875,8 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
   if (cfg->in_chans == 3) { h->mean[0] = 0.485f; h->mean[1] = 0.456f; h->mean[2] = 0.4060f; }   // (:1128)
   const char* env = getenv("HITSIR_GEMM");
   h->simt = env && strcmp(env, "simt") == 0;
+  const char* env4 = getenv("HITSIR_FFN");
+  h->ffn_unfused = env4 && strcmp(env4, "unfused") == 0;
   const char* env3 = getenv("HITSIR_SCC");
   h->scc_gram_only = env3 && strcmp(env3, "gram") == 0;
   const char* env2 = getenv("HITSIR_EPILOGUE");

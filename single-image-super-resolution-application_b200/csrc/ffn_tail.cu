@@ -1,0 +1,351 @@
+// Second half of ConvFFN fused into one persistent kernel (/root/reference/models/hit_sir_pro.py:42-46 with :15-17, and the
+// post-norm residual of HierarchicalTransformerBlock.forward :704):
+//     h2 = h1 + GELU(dwconv5x5(h1) + b_dw)            (SIMT, FP32-FMA-bound: 16 conv warps)
+//     x  = x + LayerNorm(h2 W2^T + b2)                 (tcgen05, accumulator in TMEM, LayerNorm in the epilogue)
+// The 360-channel hidden map h2 never goes to HBM: per 8 x 16 pixel tile the conv warps produce it 64 channels at a time straight
+// into the SWIZZLE_128B K-major A-operand buffers of the fc2 contraction, while the TMA producer streams the (8+4) x (16+4) x 64
+// halo boxes of h1 (zero padding = out-of-bounds fill) and the matching 64-column slices of W2.  Standalone, the depthwise conv
+// wrote and fc2 re-read 1536 B per token and fc2 sat at the HBM roofline; fused, fc2's traffic hides under the conv's FMA time.
+//
+// Warp roles (640 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = residual/output box DMA,
+// 4..19 = compute.  Compute warps 0-7 / 8-15 ("halves") convolve the even / odd 64-channel slices (one 4x4 pixel block per warp,
+// lane = channel pair, 25 taps in registers); afterwards all 16 warps run the LayerNorm epilogue (warp = TMEM lane quarter x
+// 16-column slice).  Halo stage, A buffer and W2 stage h belong to half h, so every ring is a plain two-slot ping-pong.
+#include "gemm.cuh"
+#include "kernels.cuh"
+
+namespace hitsir {
+
+namespace {
+
+constexpr int kPH = 12, kPW = 20;                         // halo patch of an 8 x 16 tile
+constexpr int kHalo = kPH * kPW * 128;                    // 30720 B, dense 128-byte pixel rows (no swizzle)
+constexpr int kDwTbl = 26 * 64 * 4;                       // 25 taps + bias of the slice's 64 channels, fp32
+constexpr int kHaloStage = 37 * 1024;                     // halo box + tap table, padded to keep the next region 1024-byte aligned
+static_assert(kHalo + kDwTbl <= kHaloStage, "halo stage");
+constexpr int kABuf = 128 * 128;                          // A operand: 128 pixels x 64 ch bf16, SWIZZLE_128B
+constexpr int kWStage = 192 * 128;                        // W2 slice: 192 rows x 64 k
+constexpr int kBoxBytes = 128 * 128;
+constexpr int kNBox = 3;
+constexpr int kOffHalo = 0;
+constexpr int kOffA = 2 * kHaloStage;
+constexpr int kOffWs = kOffA + 2 * kABuf;
+constexpr int kOffBox = kOffWs + 2 * kWStage;
+constexpr int kOffPar = kOffBox + kNBox * kBoxBytes;      // bias | gamma | beta (3 x 192 fp32)
+constexpr int kOffPart = kOffPar + 3 * 192 * 4;           // LayerNorm partials [2][4][128] float2
+constexpr int kOffBars = kOffPart + 2 * 4 * 128 * 8;
+constexpr int kNumBars = 32;
+constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + 1024;
+static_assert(kSmemBytes <= 232448, "smem budget");
+static_assert(kOffA % 1024 == 0 && kOffWs % 1024 == 0 && kOffBox % 1024 == 0, "swizzled regions need 1024-byte alignment");
+
+struct Params {
+  int B, H, W, tiles_x, tiles_y, total;
+  const float* bias;        // fc2 bias [192] (zero padded)
+  const float* gamma; const float* beta;     // norm2 [180]
+};
+
+__device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 compute warps
+
+__global__ void __launch_bounds__(640, 1)
+ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_dw, const __grid_constant__ CUtensorMap tm_w,
+                const __grid_constant__ CUtensorMap tm_x, const Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sb - smem_u32(smem_raw));
+  float* s_bias = reinterpret_cast<float*>(sp + kOffPar);
+  float* s_gamma = s_bias + 192;
+  float* s_beta = s_gamma + 192;
+  float2* s_part = reinterpret_cast<float2*>(sp + kOffPart);
+  const uint32_t bar0 = sb + kOffBars;
+  auto halo_full = [&](int h) { return bar0 + 8u * h; };
+  auto halo_empty = [&](int h) { return bar0 + 8u * (2 + h); };
+  auto a_full = [&](int h) { return bar0 + 8u * (4 + h); };
+  auto a_empty = [&](int h) { return bar0 + 8u * (6 + h); };
+  auto w_full = [&](int h) { return bar0 + 8u * (8 + h); };
+  auto w_empty = [&](int h) { return bar0 + 8u * (10 + h); };
+  auto d_full = [&](int s) { return bar0 + 8u * (12 + s); };
+  auto d_empty = [&](int s) { return bar0 + 8u * (14 + s); };
+  auto in_bar = [&](int s) { return bar0 + 8u * (16 + s); };
+  auto out_bar = [&](int s) { return bar0 + 8u * (16 + kNBox + s); };
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sp + kOffBars + kNumBars * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_h1); tma_prefetch_desc(&tm_dw); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_x); }
+  if (warp == 1 && lane == 0) {
+    for (int h = 0; h < 2; ++h) {
+      mbar_init(halo_full(h), 1); mbar_init(halo_empty(h), 8);
+      mbar_init(a_full(h), 8); mbar_init(a_empty(h), 1);
+      mbar_init(w_full(h), 1); mbar_init(w_empty(h), 1);
+      mbar_init(d_full(h), 1); mbar_init(d_empty(h), 16);
+    }
+    for (int s = 0; s < kNBox; ++s) { mbar_init(in_bar(s), 1); mbar_init(out_bar(s), 8); }   // a 32-column box is written by 2 slices x 4 quarters
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) {
+    s_bias[i] = p.bias[i];
+    s_gamma[i] = i < kC ? p.gamma[i] : 0.f;
+    s_beta[i] = i < kC ? p.beta[i] : 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_xyb = [&](int t, int* x0, int* y0, int* b) {
+    const int tx = t % p.tiles_x; const int t2 = t / p.tiles_x;
+    *x0 = tx * 16; *y0 = (t2 % p.tiles_y) * 8; *b = t2 / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== producer: per 64-channel slice one h1 halo box and one W2 slice =====================
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        for (int k = 0; k < 6; ++k) {
+          const int h = k & 1;
+          const uint32_t u = (uint32_t)(it * 3 + (k >> 1));
+          mbar_wait(halo_empty(h), (u & 1u) ^ 1u);
+          mbar_expect_tx(halo_full(h), kHalo + kDwTbl);
+          tma_load_4d(sb + kOffHalo + h * kHaloStage, &tm_h1, halo_full(h), k * 64, x0 - 2, y0 - 2, b);
+          tma_load_2d(sb + kOffHalo + h * kHaloStage + kHalo, &tm_dw, halo_full(h), k * 64, 0);
+          mbar_wait(w_empty(h), (u & 1u) ^ 1u);
+          mbar_expect_tx(w_full(h), kWStage);
+          tma_load_2d(sb + kOffWs + h * kWStage, &tm_w, w_full(h), k * 64, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer: D[128 x 192] += H2_slice[128 x 64] W2_slice^T =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 192);
+      int it = 0;
+      for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(d_empty(as), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 192);
+        for (int k = 0; k < 6; ++k) {
+          const int h = k & 1;
+          const uint32_t u = (uint32_t)(it * 3 + (k >> 1));
+          mbar_wait(a_full(h), u & 1u);
+          mbar_wait(w_full(h), u & 1u);
+          tc_fence_after();
+          const uint64_t adesc = umma_desc_sw128(sb + kOffA + h * kABuf);
+          const uint64_t bdesc = umma_desc_sw128(sb + kOffWs + h * kWStage);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, adesc + (uint64_t)(2 * kk), bdesc + (uint64_t)(2 * kk), idesc, (k | kk) != 0 ? 1u : 0u);
+          umma_commit(a_empty(h));
+          umma_commit(w_empty(h));
+        }
+        umma_commit(d_full(as));
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ===================== box DMA: residual in, updated stream out (6 boxes of 32 fp32 columns per tile) =====================
+      int c0s[kNBox], r0s[kNBox], r1s[kNBox], r2s[kNBox];
+      uint32_t u_prep = 0, u_store = 0;
+      auto store_one = [&]() {
+        const int s = (int)(u_store % kNBox);
+        mbar_wait(out_bar(s), (u_store / kNBox) & 1u);
+        tma_store_4d(&tm_x, sb + kOffBox + s * kBoxBytes, c0s[s], r0s[s], r1s[s], r2s[s]);
+        tma_commit();
+        ++u_store;
+      };
+      for (int t = blockIdx.x; t < p.total; t += gridDim.x) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        for (int j = 0; j < 6; ++j) {
+          const int s = (int)(u_prep % kNBox);
+          if (u_prep >= (uint32_t)kNBox) {
+            const uint32_t need = u_prep - (uint32_t)kNBox + 2u;
+            while (u_store < need && u_store < u_prep) store_one();
+            tma_wait_read1();                              // bulk groups retire in order: store #(u_prep - kNBox) has left the box
+          }
+          c0s[s] = 32 * j; r0s[s] = x0; r1s[s] = y0; r2s[s] = b;
+          mbar_expect_tx(in_bar(s), kBoxBytes);
+          tma_load_4d(sb + kOffBox + s * kBoxBytes, &tm_x, in_bar(s), 32 * j, x0, y0, b);
+          ++u_prep;
+        }
+      }
+      while (u_store < u_prep) store_one();
+      tma_wait_all0();
+    }
+  } else if (warp >= 4) {
+    // ===================== compute warps =====================
+    const int cw = warp - 4;
+    const int half = cw >> 3;                              // conv role: slices k = half, half + 2, half + 4
+    const int by = ((cw & 7) >> 2) * 4, bx = ((cw & 7) & 3) * 4;     // conv role: 4 x 4 block of the 8 x 16 tile
+    const int q = warp & 3, hs = cw >> 2;                  // epilogue role: TMEM lane quarter, 16-column slice of every 64-column group
+    const int r = q * 32 + lane;
+    const uint32_t rsw = (uint32_t)(r & 7);
+    uint8_t* row_ptr = sp + kOffBox + r * 128;
+    const uint32_t* halo = reinterpret_cast<const uint32_t*>(sp + kOffHalo + half * kHaloStage) + lane;      // + pixel * 32 words
+    const float2* wtab = reinterpret_cast<const float2*>(sp + kOffHalo + half * kHaloStage + kHalo) + lane;   // + tap * 32: this lane's channel pair
+    uint8_t* abuf = sp + kOffA + half * kABuf;
+    int it = 0;
+    for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+      // ---------- depthwise 5x5 + GELU + input on this half's three slices -> A operand
+#pragma unroll 1
+      for (int j = 0; j < 3; ++j) {
+        const int k = half + 2 * j;
+        const uint32_t u = (uint32_t)(it * 3 + j);
+        const int c = k * 64 + 2 * lane;
+        const bool live = c < kHid;
+        mbar_wait(halo_full(half), u & 1u);
+        const float2 bs = wtab[25 * 32];
+        float2 acc[4][4];
+#pragma unroll
+        for (int oy = 0; oy < 4; ++oy)
+#pragma unroll
+          for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = bs;
+        uint32_t center[4][4];
+        const uint32_t* tp0 = halo + (by * kPW + bx) * 32;
+#pragma unroll
+        for (int iy = 0; iy < 8; ++iy) {
+          float2 in[8];
+#pragma unroll
+          for (int ix = 0; ix < 8; ++ix) {
+            const uint32_t v = tp0[(iy * kPW + ix) * 32];
+            in[ix] = unpack_bf16x2(v);
+            if (iy >= 2 && iy < 6 && ix >= 2 && ix < 6) center[iy - 2][ix - 2] = v;
+          }
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky) {
+            const int oy = iy - ky;                        // compile-time after unrolling
+            if (oy >= 0 && oy < 4) {
+#pragma unroll
+              for (int ox = 0; ox < 4; ++ox)
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) acc[oy][ox] = __ffma2_rn(in[ox + kx], wtab[(ky * 5 + kx) * 32], acc[oy][ox]);
+            }
+          }
+        }
+        mbar_arrive_warp(halo_empty(half));                // every input word of this warp is in registers
+        mbar_wait(a_empty(half), (u & 1u) ^ 1u);           // the MMAs of the previous use of this A buffer are done
+#pragma unroll
+        for (int oy = 0; oy < 4; ++oy) {
+#pragma unroll
+          for (int ox = 0; ox < 4; ++ox) {
+            const float2 cv = unpack_bf16x2(center[oy][ox]);
+            const float2 g = gelu2(acc[oy][ox]);
+            const uint32_t o = live ? pack_bf16x2(cv.x + g.x, cv.y + g.y) : 0u;
+            const int row = (by + oy) * 16 + bx + ox;      // A row = pixel of the 8 x 16 tile
+            *reinterpret_cast<uint32_t*>(abuf + row * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(row & 7)) << 4) + (lane & 3) * 4) = o;
+          }
+        }
+        fence_proxy_async_smem();
+        mbar_arrive_warp(a_full(half));
+      }
+      // ---------- epilogue: x = x + LayerNorm(acc + b2) over the 180 real columns, 16-column slices
+      const int as = it & 1;
+      mbar_wait(d_full(as), ((uint32_t)(it >> 1)) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 192);
+      // LayerNorm statistics without cancellation: per 16-column group (mean, M2) from registers, merged with Chan's parallel update
+      // across the three groups of this thread and then across the four slices of the row
+      float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        const int c0 = 64 * g + 16 * hs;
+        float v[16];
+        tmem_ld16(tacc + c0, v);
+        const int cnt = min(16, max(0, kC - c0));
+        float sg = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { v[i] += s_bias[c0 + i]; if (i < cnt) sg += v[i]; }
+        const float mg = sg / (float)max(cnt, 1);
+        float qg = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) { const float d = v[i] - mg; if (i < cnt) qg = fmaf(d, d, qg); }
+        if (cnt > 0) {
+          const float nn = n + (float)cnt, d = mg - mean;
+          mean += d * ((float)cnt / nn);
+          m2 += qg + d * d * (n * (float)cnt / nn);
+          n = nn;
+        }
+      }
+      float2* part = s_part + (it & 1) * 512;
+      part[hs * 128 + r] = make_float2(mean, m2);
+      epi_bar_sync();
+#pragma unroll
+      for (int o = 1; o < 4; ++o) {
+        const int ho = (hs + o) & 3;
+        const float2 tv = part[ho * 128 + r];
+        const float cnt = ho == 3 ? 36.f : 48.f;           // real columns of slice ho: 3 x 16, the last slice ends at column 180
+        const float nn = n + cnt, d = tv.x - mean;
+        mean += d * (cnt / nn);
+        m2 += tv.y + d * d * (n * cnt / nn);
+        n = nn;
+      }
+      const float rstd = rsqrtf(m2 * (1.0f / (float)kC) + 1e-5f);
+#pragma unroll 1
+      for (int g = 0; g < 3; ++g) {
+        const int c0 = 64 * g + 16 * hs;
+        float v[16];
+        tmem_ld16(tacc + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = fmaf((v[i] + s_bias[c0 + i] - mean) * rstd, s_gamma[c0 + i], s_beta[c0 + i]);   // gamma = beta = 0 beyond 180
+        const uint32_t ub = (uint32_t)it * 6u + (uint32_t)(2 * g + (hs >> 1));
+        const int bb = (int)(ub % kNBox);
+        mbar_wait(in_bar(bb), (ub / kNBox) & 1u);
+        uint8_t* fb = row_ptr + bb * kBoxBytes;
+        const uint32_t ch0 = (uint32_t)((hs & 1) * 4);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          float4* ptr = reinterpret_cast<float4*>(fb + (((ch0 + (uint32_t)ch) ^ rsw) << 4));
+          const float4 rr = *ptr;
+          *ptr = make_float4(v[4 * ch] + rr.x, v[4 * ch + 1] + rr.y, v[4 * ch + 2] + rr.z, v[4 * ch + 3] + rr.w);
+        }
+        fence_proxy_async_smem();
+        mbar_arrive_warp(out_bar(bb));
+      }
+      tc_fence_before();
+      mbar_arrive_warp(d_empty(as));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace
+
+// h1: bf16 [B,H,W,384]; fc2 packed weights tensor map (box {64, 192}); x: fp32 residual stream [B,H,W,180], updated in place
+int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
+                    const float* beta, float* x, int B, int H, int W, int num_sms, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    HITSIR_CHECK(cudaFuncSetAttribute(ffn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  Params p;
+  p.B = B; p.H = H; p.W = W;
+  p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 7) / 8;
+  const long long total = (long long)B * p.tiles_x * p.tiles_y;
+  if (total > 2147483647LL / 8) { set_error("launch_ffn_tail: too many tiles"); return 1; }
+  p.total = (int)total;
+  p.bias = b2; p.gamma = gamma; p.beta = beta;
+  CUtensorMap tm_h1, tm_x, tm_dw;
+  if (make_tmap_2d_plain(&tm_dw, dw_tbl, 4, kHidp, 26, (uint64_t)kHidp * 4, 64, 26)) return 1;
+  if (make_tmap_nhwc_plain(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH)) return 1;
+  if (make_tmap_nhwc_t(&tm_x, x, 4, B, H, W, kC, kC, 32, 16, 8)) return 1;
+  const int grid = p.total < num_sms ? p.total : num_sms;
+  ffn_tail_kernel<<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_dw, tm_w2, tm_x, p);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace hitsir

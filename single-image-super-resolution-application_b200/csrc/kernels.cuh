@@ -20,6 +20,10 @@ int launch_entry_im2col(const float* x, bf16* a0, int B, int H, int W, int in_ch
 int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* out_bf16, float* out_f32, long long N, cudaStream_t st);
 // depthwise 5x5 (zero pad 2) + bias -> GELU -> + input  (ConvFFN middle, hit_sir_pro.py:42)
 int launch_dwconv5_gelu_add(const bf16* h1, const float* w_tap_major, const float* bias, bf16* h2, int B, int H, int W, int num_sms, cudaStream_t st);
+// ffn_tail.cu: dwconv5 + GELU + input fused with fc2 + LayerNorm + residual (x updated in place); tm_w2 = packed fc2 weights, box {64, 192}
+// dw_tbl: fp32 [26][384] = 25 tap rows + bias row
+int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
+                    const float* beta, float* x, int B, int H, int W, int num_sms, cudaStream_t st);
 // nearest x2 upsample of an NHWC bf16 map with C channels
 int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st);
 int launch_fill_f32(float* p, float v, long long n, cudaStream_t st);

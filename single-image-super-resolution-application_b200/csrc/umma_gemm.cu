@@ -226,6 +226,22 @@ int make_tmap_nhwc_t(CUtensorMap* m, const void* base, int elem_bytes, int B, in
   return 0;
 }
 
+// 2-D map without shared-memory swizzle (dense box rows)
+int make_tmap_2d_plain(CUtensorMap* m, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                       uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return 1;
+  const CUtensorMapDataType dt = elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, dt, 2, const_cast<void*>(base), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(2d plain) failed with CUresult %d", (int)r); return 1; }
+  return 0;
+}
+
 // bf16 NHWC map without shared-memory swizzle (dense 2*box_c-byte pixel rows), OOB = zero fill
 int make_tmap_nhwc_plain(CUtensorMap* m, const void* base, int B, int H, int W, int C, uint32_t box_c, uint32_t box_w, uint32_t box_h) {
   PFN_encodeTiled enc = get_encode();
