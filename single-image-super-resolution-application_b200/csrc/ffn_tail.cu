@@ -259,14 +259,21 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         const int c0 = 64 * g + 16 * hs;
         float v[16];
         tmem_ld16(tacc + c0, v);
-        const int cnt = min(16, max(0, kC - c0));
-        float sg = 0.f;
+        const int cnt = min(16, max(0, kC - c0));          // 16 except for the last slice of the last group (4 real columns)
+        float sg = 0.f, qg = 0.f, mg;
+        if (cnt == 16) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { v[i] += s_bias[c0 + i]; if (i < cnt) sg += v[i]; }
-        const float mg = sg / (float)max(cnt, 1);
-        float qg = 0.f;
+          for (int i = 0; i < 16; ++i) { v[i] += s_bias[c0 + i]; sg += v[i]; }
+          mg = sg * (1.0f / 16.0f);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) { const float d = v[i] - mg; if (i < cnt) qg = fmaf(d, d, qg); }
+          for (int i = 0; i < 16; ++i) { const float d = v[i] - mg; qg = fmaf(d, d, qg); }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { v[i] += s_bias[c0 + i]; if (i < cnt) sg += v[i]; }
+          mg = sg / (float)max(cnt, 1);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) { const float d = v[i] - mg; if (i < cnt) qg = fmaf(d, d, qg); }
+        }
         if (cnt > 0) {
           const float nn = n + (float)cnt, d = mg - mean;
           mean += d * ((float)cnt / nn);

@@ -270,35 +270,59 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         for (int i = 0; i < SW; ++i) x1[i] += s_bias[n0 + 128 + ci0 + i];
       }
       if (p.epi == EPI_LN) {
-        // one pass: sum and sum of squares of this thread's slices of the row, combined with the partner warps
-        float s = 0.f, ss = 0.f;
+        // statistics without cancellation (sum-of-squares minus mean^2 loses everything when |mean| >> std, which the stress weights
+        // provoke): per slice (mean, M2) from registers, merged with Chan's parallel update across groups and partner warps
+        auto slice_count = [&](int ho) {
+          int cn = 0;
+          for (int g = 0; g < Cfg::kGroups; ++g) cn += min(SW, max(0, p.n_real - (64 * g + SW * ho)));
+          return cn;
+        };
+        float n = 0.f;
+        mean = 0.f;
+        float m2 = 0.f;
 #pragma unroll 1
         for (int g = 0; g < Cfg::kGroups; ++g) {
           const int c0 = 64 * g + SW * hs;
           float v[SW];
           ld_slice(tacc + c0, v);
+          const int cnt = min(SW, max(0, p.n_real - c0));
+          float sg = 0.f, qg = 0.f, mg;
+          if (cnt == SW) {
 #pragma unroll
-          for (int i = 0; i < SW; i += 4) {
-            const float4 bb = *reinterpret_cast<const float4*>(s_bias + n0 + c0 + i);
-            const float t0 = v[i] + bb.x, t1 = v[i + 1] + bb.y, t2 = v[i + 2] + bb.z, t3 = v[i + 3] + bb.w;
-            if (c0 + i < p.n_real) { s += t0; ss = fmaf(t0, t0, ss); }
-            if (c0 + i + 1 < p.n_real) { s += t1; ss = fmaf(t1, t1, ss); }
-            if (c0 + i + 2 < p.n_real) { s += t2; ss = fmaf(t2, t2, ss); }
-            if (c0 + i + 3 < p.n_real) { s += t3; ss = fmaf(t3, t3, ss); }
+            for (int i = 0; i < SW; ++i) { v[i] += s_bias[n0 + c0 + i]; sg += v[i]; }
+            mg = sg * (1.0f / (float)SW);
+#pragma unroll
+            for (int i = 0; i < SW; ++i) { const float d = v[i] - mg; qg = fmaf(d, d, qg); }
+          } else {
+#pragma unroll
+            for (int i = 0; i < SW; ++i) { v[i] += s_bias[n0 + c0 + i]; if (i < cnt) sg += v[i]; }
+            mg = sg / (float)max(cnt, 1);
+#pragma unroll
+            for (int i = 0; i < SW; ++i) { const float d = v[i] - mg; if (i < cnt) qg = fmaf(d, d, qg); }
+          }
+          if (cnt > 0) {
+            const float nn = n + (float)cnt, d = mg - mean;
+            mean += d * ((float)cnt / nn);
+            m2 += qg + d * d * (n * (float)cnt / nn);
+            n = nn;
           }
         }
         float2* part = s_part + (it & 1) * (EQ * 128);
-        part[hs * 128 + r] = make_float2(s, ss);
+        part[hs * 128 + r] = make_float2(mean, m2);
         epi_bar_sync<128 * EQ>();
 #pragma unroll
         for (int o = 1; o < EQ; ++o) {
-          const float2 t = part[((hs + o) % EQ) * 128 + r];
-          s += t.x; ss += t.y;
+          const int ho = (hs + o) % EQ;
+          const float cnt = (float)slice_count(ho);
+          if (cnt > 0.f) {
+            const float2 t = part[ho * 128 + r];
+            const float nn = n + cnt, d = t.x - mean;
+            mean += d * (cnt / nn);
+            m2 += t.y + d * d * (n * cnt / nn);
+            n = nn;
+          }
         }
-        const float inv_n = 1.0f / (float)p.n_real;
-        mean = s * inv_n;
-        const float var = fmaxf(ss * inv_n - mean * mean, 0.f);
-        rstd = rsqrtf(var + 1e-5f);
+        rstd = rsqrtf(m2 / (float)p.n_real + 1e-5f);
       }
 #pragma unroll 1
       for (int g = 0; g < Cfg::kGroups; ++g) {
