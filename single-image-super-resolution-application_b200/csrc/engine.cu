@@ -89,6 +89,7 @@ struct HitsirHandle {
   int device = 0;
   int num_sms = 148;
   bool simt = false;
+  bool no_epilogue_stats = false; // HITSIR_STATS=kernel: always compute the casa statistics with the stand-alone sca_stats pass
   bool ffn_unfused = false;       // HITSIR_FFN=unfused: separate dwconv5 and fc2 kernels for every block
   bool scc_gram_only = false;     // HITSIR_SCC=gram: use the Gram-matrix kernel (scc_umma.cu) for every window size
   bool direct_epilogue = false;   // HITSIR_EPILOGUE=direct: per-row global stores instead of the TMA-staged epilogue
@@ -495,8 +496,11 @@ int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Wor
   ws->cavg = b.take<float>(np_max);
   ws->cmax = b.take<float>(np_max);
   ws->nparts = 64;
-  ws->part_sum = b.take<float>((size_t)B * ws->nparts * kC);
-  ws->part_max = b.take<float>((size_t)B * ws->nparts * kC);
+  {
+    const size_t np = (size_t)(ffn_tiles_per_image(H, W) > ws->nparts ? ffn_tiles_per_image(H, W) : ws->nparts);   // ffn_tail emits one partial per 8x16 tile
+    ws->part_sum = b.take<float>((size_t)B * np * kC);
+    ws->part_max = b.take<float>((size_t)B * np * kC);
+  }
   ws->s1 = b.take<float>((size_t)B * kC);
   ws->s2 = b.take<float>((size_t)B * kC);
   ws->scc_dbg = b.take<float>((size_t)kSccDbgFloats);
@@ -534,6 +538,7 @@ struct Fwd {
   long long N;
   Workspace ws;
   bool stopped = false;
+  int stats_nparts = 0;      // > 0: casa statistics of the current stream were produced by the previous block's ffn_tail (partials per image)
 };
 
 // returns 1 on error, sets f.stopped when the requested tap asked to stop
@@ -652,9 +657,14 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   g.nWy = g.pg.Hp / w; g.nWx = g.pg.Wp / w; g.parts = 1;
   const long long Np = (long long)f.B * g.pg.Hp * g.pg.Wp;
   if (c.is_channel_spatial_attn) {
-    LAUNCH("sca_stats", 1, launch_sca_stats(xin, g.pg, ws.cavg, ws.cmax, ws.part_sum, ws.part_max, ws.nparts, f.st));
-    LAUNCH("sca_mlp", 1, launch_sca_mlp(ws.part_sum, ws.part_max, ws.nparts, g.pg, bw.casa, ws.s1, ws.s2, f.st));
+    int nparts = f.stats_nparts;
+    if (nparts == 0) {       // no producer epilogue delivered them (first block of a layer, unfused fallback): one pass over the stream
+      nparts = ws.nparts;
+      LAUNCH("sca_stats", 1, launch_sca_stats(xin, g.pg, ws.cavg, ws.cmax, ws.part_sum, ws.part_max, nparts, f.st));
+    }
+    LAUNCH("sca_mlp", 1, launch_sca_mlp(ws.part_sum, ws.part_max, nparts, g.pg, bw.casa, ws.s1, ws.s2, f.st));
   }
+  f.stats_nparts = 0;
   LAUNCH("qkv_build", 1, launch_qkv_build(xin, g.pg, c.is_channel_spatial_attn, ws.cavg, ws.cmax, ws.s1, ws.s2, bw.casa, ws.T, f.st));
   TAPP((tn + ".qkv").c_str(), ws.T, 1, kCp, Np, kC);
   {
@@ -679,9 +689,18 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   p.epi = EPI_STORE; p.act = ACT_GELU; p.n_real = kHid; p.out_bf16 = ws.H1; p.ldb = kHidp;
   RUN(linear(f, "gemm_fc1_gelu", bw.fc1, ws.xb0, f.N, p));
   const bool need_shadow = (j == c.depths[i] - 1);      // the RHTB conv after the last block reads a bf16 shadow of the stream (:934)
-  if (!h->simt && !h->direct_epilogue && !h->ffn_unfused && !need_shadow) {
+  if (!h->simt && !h->direct_epilogue && !h->ffn_unfused) {
     // dwconv5 + GELU + input, fc2, norm2 and the residual add in one kernel: the hidden map h2 never reaches HBM
-    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_w, bw.fc2.tm, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, h->num_sms, f.st));
+    // ... and, when another block of this layer follows, the casa statistics of the new stream for that block's window padding
+    FfnStats fs; const FfnStats* fsp = nullptr;
+    if (c.is_channel_spatial_attn && !need_shadow && !h->no_epilogue_stats) {
+      const int wn = h->blocks[i][j + 1].win;
+      fs = FfnStats{ws.cavg, ws.cmax, ws.part_sum, ws.part_max, round_up(f.H, wn), round_up(f.W, wn)};
+      fsp = &fs;
+    }
+    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_w, bw.fc2.tm, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, fsp, h->num_sms, f.st));
+    if (fsp != nullptr) f.stats_nparts = ffn_tiles_per_image(f.H, f.W);
+    if (need_shadow) LAUNCH("cast_shadow", 1, launch_cast_rows_bf16(xout, ws.xb0, f.N, f.st));
   } else {
     LAUNCH("dwconv5", 1, launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, h->num_sms, f.st));
     // fc2 + norm2 + residual (:704)
@@ -875,6 +894,8 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
   if (cfg->in_chans == 3) { h->mean[0] = 0.485f; h->mean[1] = 0.456f; h->mean[2] = 0.4060f; }   // (:1128)
   const char* env = getenv("HITSIR_GEMM");
   h->simt = env && strcmp(env, "simt") == 0;
+  const char* env5 = getenv("HITSIR_STATS");
+  h->no_epilogue_stats = env5 && strcmp(env5, "kernel") == 0;
   const char* env4 = getenv("HITSIR_FFN");
   h->ffn_unfused = env4 && strcmp(env4, "unfused") == 0;
   const char* env3 = getenv("HITSIR_SCC");

@@ -33,8 +33,10 @@ constexpr int kOffWs = kOffA + 2 * kABuf;
 constexpr int kOffBox = kOffWs + 2 * kWStage;
 constexpr int kOffPar = kOffBox + kNBox * kBoxBytes;      // bias | gamma | beta (3 x 192 fp32)
 constexpr int kOffPart = kOffPar + 3 * 192 * 4;           // LayerNorm partials [2][4][128] float2
-constexpr int kOffBars = kOffPart + 2 * 4 * 128 * 8;
-constexpr int kNumBars = 32;
+constexpr int kOffPart2 = kOffPart + 2 * 4 * 128 * 8;      // per-pixel channel (sum, max) partials [4][128] float2
+constexpr int kOffMult = kOffPart2 + 2 * 4 * 128 * 8;     // (double-buffered by tile parity); reflect multiplicity of the tile's 128 pixels (0 = outside the image)
+constexpr int kOffBars = kOffMult + 128 * 4;
+constexpr int kNumBars = 40;
 constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "smem budget");
 static_assert(kOffA % 1024 == 0 && kOffWs % 1024 == 0 && kOffBox % 1024 == 0, "swizzled regions need 1024-byte alignment");
@@ -43,7 +45,12 @@ struct Params {
   int B, H, W, tiles_x, tiles_y, total;
   const float* bias;        // fc2 bias [192] (zero padded)
   const float* gamma; const float* beta;     // norm2 [180]
+  // casa statistics of the block output for the next block (SpatialChannelAttention :345-349), all optional (nullptr = off):
+  float* cavg; float* cmax;                  // per pixel channel mean / max, [B*H*W]
+  float* part_sum; float* part_max;          // per tile per channel: reflect-weighted sum / max over the tile's pixels, [total][180]
+  int Hp, Wp;                                // reflect-padded size of the NEXT block's window grid
 };
+__device__ __forceinline__ int reflect_mult(int i, int n, int np) { return 1 + ((i >= 2 * (n - 1) - (np - 1) && i <= n - 2) ? 1 : 0); }
 
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(tmap), "r"(src), "r"(c0), "r"(c1),
@@ -64,6 +71,9 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
   float* s_gamma = s_bias + 192;
   float* s_beta = s_gamma + 192;
   float2* s_part = reinterpret_cast<float2*>(sp + kOffPart);
+  float2* s_part2 = reinterpret_cast<float2*>(sp + kOffPart2);
+  float* s_mult = reinterpret_cast<float*>(sp + kOffMult);
+  const bool want_stats = p.cavg != nullptr;
   const uint32_t bar0 = sb + kOffBars;
   auto halo_full = [&](int h) { return bar0 + 8u * h; };
   auto halo_empty = [&](int h) { return bar0 + 8u * (2 + h); };
@@ -75,6 +85,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
   auto d_empty = [&](int s) { return bar0 + 8u * (14 + s); };
   auto in_bar = [&](int s) { return bar0 + 8u * (16 + s); };
   auto out_bar = [&](int s) { return bar0 + 8u * (16 + kNBox + s); };
+  auto red_done = [&](int s) { return bar0 + 8u * (16 + 2 * kNBox + s); };      // statistics warp -> DMA: box s has been reduced
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sp + kOffBars + kNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -86,10 +97,10 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
       mbar_init(w_full(h), 1); mbar_init(w_empty(h), 1);
       mbar_init(d_full(h), 1); mbar_init(d_empty(h), 16);
     }
-    for (int s = 0; s < kNBox; ++s) { mbar_init(in_bar(s), 1); mbar_init(out_bar(s), 8); }   // a 32-column box is written by 2 slices x 4 quarters
+    for (int s = 0; s < kNBox; ++s) { mbar_init(in_bar(s), 1); mbar_init(out_bar(s), 8); mbar_init(red_done(s), 1); }   // a 32-column box is written by 2 slices x 4 quarters
     fence_barrier_init();
   }
-  if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
+  if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }   // warp 2 later doubles as the statistics warp
   for (int i = threadIdx.x; i < 192; i += blockDim.x) {
     s_bias[i] = p.bias[i];
     s_gamma[i] = i < kC ? p.gamma[i] : 0.f;
@@ -150,6 +161,50 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         umma_commit(d_full(as));
       }
     }
+  } else if (warp == 2) {
+    // ===================== statistics warp (only with casa statistics on): reflect-weighted channel sums / maxima of every finished
+    // 32-column box over its 128 pixels, for the next block's global pools.  lane = (row phase lane >> 3, 16-byte chunk lane & 7).
+    if (want_stats) {
+      uint32_t u = 0;
+      for (int t = blockIdx.x; t < p.total; t += gridDim.x) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        for (int rr = lane; rr < 128; rr += 32) {
+          const int y = y0 + (rr >> 4), x = x0 + (rr & 15);
+          s_mult[rr] = (y < p.H && x < p.W) ? (float)(reflect_mult(y, p.H, p.Hp) * reflect_mult(x, p.W, p.Wp)) : 0.f;
+        }
+        __syncwarp();
+        for (int j = 0; j < 6; ++j, ++u) {
+          const int s = (int)(u % kNBox);
+          mbar_wait(out_bar(s), (u / kNBox) & 1u);
+          const uint8_t* box = sp + kOffBox + s * kBoxBytes;
+          const int ck = lane & 7, rph = lane >> 3;
+          float4 sum = make_float4(0.f, 0.f, 0.f, 0.f), mx = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll 4
+          for (int r4 = 0; r4 < 128; r4 += 4) {
+            const int rr = r4 + rph;
+            const float m = s_mult[rr];
+            const float4 v = *reinterpret_cast<const float4*>(box + rr * 128 + (((uint32_t)ck ^ (uint32_t)(rr & 7)) << 4));
+            sum.x = fmaf(m, v.x, sum.x); sum.y = fmaf(m, v.y, sum.y); sum.z = fmaf(m, v.z, sum.z); sum.w = fmaf(m, v.w, sum.w);
+            if (m > 0.f) { mx.x = fmaxf(mx.x, v.x); mx.y = fmaxf(mx.y, v.y); mx.z = fmaxf(mx.z, v.z); mx.w = fmaxf(mx.w, v.w); }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(red_done(s));          // every lane has read the box: it may be recycled once its store has drained too
+#pragma unroll
+          for (int o = 8; o <= 16; o <<= 1) {              // fixed-order merge of the four row phases: deterministic
+            sum.x += __shfl_xor_sync(0xffffffffu, sum.x, o); sum.y += __shfl_xor_sync(0xffffffffu, sum.y, o);
+            sum.z += __shfl_xor_sync(0xffffffffu, sum.z, o); sum.w += __shfl_xor_sync(0xffffffffu, sum.w, o);
+            mx.x = fmaxf(mx.x, __shfl_xor_sync(0xffffffffu, mx.x, o)); mx.y = fmaxf(mx.y, __shfl_xor_sync(0xffffffffu, mx.y, o));
+            mx.z = fmaxf(mx.z, __shfl_xor_sync(0xffffffffu, mx.z, o)); mx.w = fmaxf(mx.w, __shfl_xor_sync(0xffffffffu, mx.w, o));
+          }
+          const int col = 32 * j + 4 * ck;
+          if (rph == 0 && col < kC) {                      // 180 = 45 chunks: a chunk is entirely real or entirely padding
+            *reinterpret_cast<float4*>(p.part_sum + (long long)t * kC + col) = sum;
+            *reinterpret_cast<float4*>(p.part_max + (long long)t * kC + col) = mx;
+          }
+        }
+        __syncwarp();                                       // s_mult is rewritten for the next tile
+      }
+    }
   } else if (warp == 3) {
     if (lane == 0) {
       // ===================== box DMA: residual in, updated stream out (6 boxes of 32 fp32 columns per tile) =====================
@@ -170,6 +225,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
             const uint32_t need = u_prep - (uint32_t)kNBox + 2u;
             while (u_store < need && u_store < u_prep) store_one();
             tma_wait_read1();                              // bulk groups retire in order: store #(u_prep - kNBox) has left the box
+            if (want_stats) mbar_wait(red_done(s), ((u_prep / kNBox) - 1u) & 1u);   // ... and the statistics warp has read it
           }
           c0s[s] = 32 * j; r0s[s] = x0; r1s[s] = y0; r2s[s] = b;
           mbar_expect_tx(in_bar(s), kBoxBytes);
@@ -192,7 +248,22 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
     const uint32_t* halo = reinterpret_cast<const uint32_t*>(sp + kOffHalo + half * kHaloStage) + lane;      // + pixel * 32 words
     const float2* wtab = reinterpret_cast<const float2*>(sp + kOffHalo + half * kHaloStage + kHalo) + lane;   // + tap * 32: this lane's channel pair
     uint8_t* abuf = sp + kOffA + half * kABuf;
-    int it = 0;
+    // per-pixel channel mean / max of a finished tile (the casa gate's 3x3 convs read them, :345-347): the four slice partials of a row
+    // are exchanged through s_part2 and flushed by the hs == 0 thread after the NEXT barrier of the compute warps (no extra barrier)
+    auto flush_pixel_stats = [&](int tprev, int itprev) {
+      if (hs != 0) return;
+      int x0, y0, b; tile_xyb(tprev, &x0, &y0, &b);
+      const int y = y0 + (r >> 4), x = x0 + (r & 15);
+      if (y >= p.H || x >= p.W) return;
+      const float2* pp = s_part2 + (itprev & 1) * 512;
+      float ls = 0.f, lm = -INFINITY;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) { const float2 tv = pp[o * 128 + r]; ls += tv.x; lm = fmaxf(lm, tv.y); }
+      const long long pix = ((long long)b * p.H + y) * p.W + x;
+      p.cavg[pix] = ls * (1.0f / (float)kC);
+      p.cmax[pix] = lm;
+    };
+    int it = 0, tprev = -1;
     for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
       // ---------- depthwise 5x5 + GELU + input on this half's three slices -> A operand
 #pragma unroll 1
@@ -284,6 +355,8 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
       float2* part = s_part + (it & 1) * 512;
       part[hs * 128 + r] = make_float2(mean, m2);
       epi_bar_sync();
+      if (want_stats && tprev >= 0) flush_pixel_stats(tprev, it - 1);
+      tprev = t;
 #pragma unroll
       for (int o = 1; o < 4; ++o) {
         const int ho = (hs + o) & 3;
@@ -295,6 +368,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         n = nn;
       }
       const float rstd = rsqrtf(m2 * (1.0f / (float)kC) + 1e-5f);
+      float ls = 0.f, lm = -INFINITY;                       // channel sum / max of this thread's real output columns
 #pragma unroll 1
       for (int g = 0; g < 3; ++g) {
         const int c0 = 64 * g + 16 * hs;
@@ -311,14 +385,21 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         for (int ch = 0; ch < 4; ++ch) {
           float4* ptr = reinterpret_cast<float4*>(fb + (((ch0 + (uint32_t)ch) ^ rsw) << 4));
           const float4 rr = *ptr;
-          *ptr = make_float4(v[4 * ch] + rr.x, v[4 * ch + 1] + rr.y, v[4 * ch + 2] + rr.z, v[4 * ch + 3] + rr.w);
+          const float4 o = make_float4(v[4 * ch] + rr.x, v[4 * ch + 1] + rr.y, v[4 * ch + 2] + rr.z, v[4 * ch + 3] + rr.w);
+          *ptr = o;
+          if (c0 + 4 * ch < kC) {                           // 180 = 45 chunks of 4: a chunk is entirely real or entirely padding
+            ls += (o.x + o.y) + (o.z + o.w);
+            lm = fmaxf(lm, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+          }
         }
         fence_proxy_async_smem();
         mbar_arrive_warp(out_bar(bb));
       }
       tc_fence_before();
       mbar_arrive_warp(d_empty(as));
+      if (want_stats) s_part2[(it & 1) * 512 + hs * 128 + r] = make_float2(ls, lm);   // flushed after the next tile's LayerNorm barrier
     }
+    if (want_stats && tprev >= 0) { epi_bar_sync(); flush_pixel_stats(tprev, it - 1); }
   }
   tc_fence_before();
   __syncthreads();
@@ -332,7 +413,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
 
 // h1: bf16 [B,H,W,384]; fc2 packed weights tensor map (box {64, 192}); x: fp32 residual stream [B,H,W,180], updated in place
 int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
-                    const float* beta, float* x, int B, int H, int W, int num_sms, cudaStream_t st) {
+                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     HITSIR_CHECK(cudaFuncSetAttribute(ffn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
@@ -345,6 +426,8 @@ int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const CUtensorMap& tm_w
   if (total > 2147483647LL / 8) { set_error("launch_ffn_tail: too many tiles"); return 1; }
   p.total = (int)total;
   p.bias = b2; p.gamma = gamma; p.beta = beta;
+  p.cavg = p.cmax = p.part_sum = p.part_max = nullptr; p.Hp = H; p.Wp = W;
+  if (stats != nullptr) { p.cavg = stats->cavg; p.cmax = stats->cmax; p.part_sum = stats->part_sum; p.part_max = stats->part_max; p.Hp = stats->Hp; p.Wp = stats->Wp; }
   CUtensorMap tm_h1, tm_x, tm_dw;
   if (make_tmap_2d_plain(&tm_dw, dw_tbl, 4, kHidp, 26, (uint64_t)kHidp * 4, 64, 26)) return 1;
   if (make_tmap_nhwc_plain(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH)) return 1;

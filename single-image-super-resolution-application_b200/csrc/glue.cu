@@ -10,6 +10,8 @@ namespace hitsir {
 namespace {
 
 __device__ __forceinline__ int reflect_src(int i, int n) { return i < n ? i : 2 * (n - 1) - i; }   // F.pad 'reflect' (:672)
+// number of positions of the padded axis [0, np) that read source index i: padded ip in [n, np) mirrors to 2(n-1) - ip
+__device__ __forceinline__ int reflect_mult(int i, int n, int np) { return 1 + ((i >= 2 * (n - 1) - (np - 1) && i <= n - 2) ? 1 : 0); }
 
 // ---------------------------------------------------------------------------------------------
 __global__ void entry_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ a0, int B, int H, int W, int in_ch, int f, int Kp,
@@ -191,6 +193,23 @@ __global__ void tap_kernel(const void* src, int is_bf16, int ld, float* dst, lon
   }
 }
 
+// bf16 [N,192] shadow (pad 0) of an fp32 [N,180] stream: thread = (row, 8 channels)
+__global__ void cast_rows_bf16_kernel(const float* __restrict__ a, bf16* __restrict__ out, long long N) {
+  constexpr int groups = kCp / 8;
+  const long long total = N * groups;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups; const int c0 = (int)(i - r * groups) * 8;
+    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (c0 < kC) {
+      const float4 v0 = *reinterpret_cast<const float4*>(a + r * kC + c0);
+      v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w;
+      if (c0 + 4 < kC) { const float4 v1 = *reinterpret_cast<const float4*>(a + r * kC + c0 + 4); v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w; }
+    }
+    *reinterpret_cast<uint4*>(out + r * kCp + c0) =
+        make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
 __global__ void add_to_bf16_kernel(const float* __restrict__ a, const float* __restrict__ b, bf16* __restrict__ out, long long N) {
   const long long total = N * kCp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -205,11 +224,13 @@ __global__ void add_to_bf16_kernel(const float* __restrict__ a, const float* __r
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sca_stats_kernel(const float* __restrict__ x, PadGeom g, float* __restrict__ cavg, float* __restrict__ cmax,
                                                         float* __restrict__ part_sum, float* __restrict__ part_max, int nparts) {
+  // cavg / cmax are stored for the UNPADDED pixels (the casa gate gathers them through the reflect map); the global pools run over
+  // the reflect-padded map (:348-349 on the padded x of :554-557), i.e. every pixel counts once per padded position that mirrors it.
   __shared__ float s_sum[8][kCp];
   __shared__ float s_max[8][kCp];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, part = blockIdx.x;
-  const int npix = g.Hp * g.Wp;
+  const int npix = g.H * g.W;
   const int per = (npix + nparts - 1) / nparts;
   const int p0 = part * per, p1 = min(npix, p0 + per);
   float asum[6], amax[6];
@@ -221,8 +242,7 @@ __global__ void __launch_bounds__(256) sca_stats_kernel(const float* __restrict_
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
       const int pp = min(pp0 + u, p1 - 1);
-      const int yp = pp / g.Wp, xp = pp - yp * g.Wp;
-      const float* r = x + (((long long)b * g.H + reflect_src(yp, g.H)) * g.W + reflect_src(xp, g.W)) * kC;
+      const float* r = x + ((long long)b * npix + pp) * kC;
 #pragma unroll
       for (int i = 0; i < 6; ++i) { const int c = lane + 32 * i; v[u][i] = c < kC ? r[c] : 0.f; }
     }
@@ -230,11 +250,13 @@ __global__ void __launch_bounds__(256) sca_stats_kernel(const float* __restrict_
     for (int u = 0; u < 4; ++u) {
       const int pp = pp0 + u;
       if (pp >= p1) break;
+      const int y = pp / g.W, xw = pp - y * g.W;
+      const float mult = (float)(reflect_mult(y, g.H, g.Hp) * reflect_mult(xw, g.W, g.Wp));
       float s = 0.f, m = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
         const int c = lane + 32 * i;
-        if (c < kC) { s += v[u][i]; m = fmaxf(m, v[u][i]); asum[i] += v[u][i]; amax[i] = fmaxf(amax[i], v[u][i]); }
+        if (c < kC) { s += v[u][i]; m = fmaxf(m, v[u][i]); asum[i] = fmaf(mult, v[u][i], asum[i]); amax[i] = fmaxf(amax[i], v[u][i]); }
       }
       s = warp_sum(s); m = warp_max(m);
       if (lane == 0) { cavg[(long long)b * npix + pp] = s / (float)kC; cmax[(long long)b * npix + pp] = m; }
@@ -310,14 +332,15 @@ __global__ void __launch_bounds__(96, 10) qkv_casa_kernel(const float* __restric
   const int run = blockIdx.x % runs; const int t2 = blockIdx.x / runs;
   const int yp = t2 % g.Hp; const int b = t2 / g.Hp;
   const int xs = run * kQkvRun;
-  const float* ca = cavg + (long long)b * g.Hp * g.Wp;
-  const float* cm = cmax + (long long)b * g.Hp * g.Wp;
+  const float* ca = cavg + (long long)b * g.H * g.W;      // statistics of the unpadded pixels, gathered through the reflect map
+  const float* cm = cmax + (long long)b * g.H * g.W;
   for (int i = threadIdx.x; i < 3 * (kQkvRun + 2); i += 96) {
     const int rr = i / (kQkvRun + 2), cc = i - rr * (kQkvRun + 2);
     const int yy = yp + rr - 1, xx = xs + cc - 1;
     const bool ok = yy >= 0 && yy < g.Hp && xx >= 0 && xx < g.Wp;     // zero padding of the PADDED map
-    sa[rr][cc] = ok ? ca[yy * g.Wp + xx] : 0.f;
-    sm[rr][cc] = ok ? cm[yy * g.Wp + xx] : 0.f;
+    const int src = ok ? reflect_src(yy, g.H) * g.W + reflect_src(xx, g.W) : 0;
+    sa[rr][cc] = ok ? ca[src] : 0.f;
+    sm[rr][cc] = ok ? cm[src] : 0.f;
   }
   const int pos = 2 * threadIdx.x;
   const int cA = scc_chan(pos), cb = scc_chan(pos + 1);
@@ -566,6 +589,11 @@ int launch_fill_f32(float* p, float v, long long n, cudaStream_t st) {
 }
 int launch_f32_to_f32_tap(const void* src, int is_bf16, int ld, float* dst, long long rows, int cols, int perm, cudaStream_t st) {
   tap_kernel<<<grid_for(rows * cols, 256), 256, 0, st>>>(src, is_bf16, ld, dst, rows, cols, perm);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_cast_rows_bf16(const float* a, bf16* out, long long N, cudaStream_t st) {
+  cast_rows_bf16_kernel<<<grid_for(N * (kCp / 8), 256), 256, 0, st>>>(a, out, N);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

@@ -21,14 +21,20 @@ int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* 
 // depthwise 5x5 (zero pad 2) + bias -> GELU -> + input  (ConvFFN middle, hit_sir_pro.py:42)
 int launch_dwconv5_gelu_add(const bf16* h1, const float* w_tap_major, const float* bias, bf16* h2, int B, int H, int W, int num_sms, cudaStream_t st);
 // ffn_tail.cu: dwconv5 + GELU + input fused with fc2 + LayerNorm + residual (x updated in place); tm_w2 = packed fc2 weights, box {64, 192}
+// Optional by-product of ffn_tail: the casa statistics of the block output for the NEXT block (padded to Hp x Wp there):
+// cavg/cmax [B*H*W], part_sum/part_max [B * tiles][180] with tiles = ceil(H/8) * ceil(W/16) 8x16-pixel tiles per image
+struct FfnStats { float* cavg; float* cmax; float* part_sum; float* part_max; int Hp, Wp; };
+inline int ffn_tiles_per_image(int H, int W) { return ((H + 7) / 8) * ((W + 15) / 16); }
 // dw_tbl: fp32 [26][384] = 25 tap rows + bias row
 int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
-                    const float* beta, float* x, int B, int H, int W, int num_sms, cudaStream_t st);
+                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st);
 // nearest x2 upsample of an NHWC bf16 map with C channels
 int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st);
 int launch_fill_f32(float* p, float v, long long n, cudaStream_t st);
 // perm != 0: column c is read from the head-padded position scc_pos(c)
 int launch_f32_to_f32_tap(const void* src, int src_is_bf16, int ld_src, float* dst, long long rows, int cols, int perm, cudaStream_t st);
+// out_bf16[N,192] = bf16(a) (pad 0): GEMM operand shadow of the fp32 stream
+int launch_cast_rows_bf16(const float* a, bf16* out, long long N, cudaStream_t st);
 // out_bf16[N,192] = bf16(a + b) (fusion disabled path, hit_sir_pro.py:1153)
 int launch_add_to_bf16(const float* a, const float* b, bf16* out, long long N, cudaStream_t st);
 
