@@ -164,3 +164,18 @@ def test_full_size_batch_properties():
     assert torch.equal(y, run_cuda(model, x))
     y1 = run_cuda(model, x[1:2])
     assert (y[1:2] - y1).abs().max().item() < 1e-5
+
+
+def test_host_pipeline_matches_forward():
+    """Double-buffered host<->device pipeline (three batches through two slots) returns exactly what forward does."""
+    from hitsir_b200 import HostPipeline
+    model, _ = build_pair((1, 1, 1), "nearest+conv", 4, "init", 111)
+    xs = [synthetic_image(2, 40, 48, seed=20 + i) for i in range(3)]
+    ys = [run_cuda(model, x) for x in xs]
+    pipe = HostPipeline(model, DEV)
+    outs = [torch.empty_like(y).pin_memory() for y in ys]
+    for x, o in zip(xs, outs):
+        pipe.submit(x.pin_memory(), o)
+    pipe.wait()
+    for y, o in zip(ys, outs):
+        assert torch.equal(y, o)
