@@ -86,6 +86,7 @@ def category_flops(cat, B, H, W):
         "conv_hr": 2 * 16 * N * 9 * 64 * 64, "conv_last": 2 * 16 * N * 9 * 64 * 3,
         "gemm_first_msgate": 2 * N * 3 * 180 * (9 + 25 + 49 + 81 + 1), "gemm_first_last": 2 * N * 720 * 180,
         "gemm_first": 2 * N * 27 * 180,
+        "ffn_tail": 2 * N * 360 * 180 + 2 * N * 360 * 25,          # fc2 + the depthwise 5x5 (both counted by the reference flop counter)
     }
     if cat in table:
         return table[cat]
@@ -105,6 +106,8 @@ def category_bytes(cat, B, H, W):
     N = B * H * W
     table = {
         "dwconv5": N * (360 * 2 + 360 * 2),                       # bf16 hidden in, bf16 hidden out
+        "ffn_tail": N * (360 * 2 + 180 * 4 + 180 * 4),            # bf16 hidden in, fp32 residual in, fp32 stream out
+        "cast_shadow": N * (180 * 4 + 180 * 2),
         "qkv_build": N * (180 * 4 + 180 * 2),                     # fp32 stream in, bf16 window tokens out
         "sca_stats": N * 180 * 4,                                 # fp32 stream in (statistics out are negligible)
         "gemm_proj_ln": N * (180 * 2 + 180 * 4 + 180 * 4 + 180 * 2),   # bf16 A, fp32 residual in, fp32 stream + bf16 shadow out
@@ -210,6 +213,7 @@ def run_ours(args):
     cat, (cat_ms, cat_n) = max(prof.items(), key=lambda kv: kv[1][0])
     fl = category_flops(cat, B, H, W)
     by = category_bytes(cat, B, H, W)
+    N_tok = B * H * W
     t_launch = cat_ms / cat_n / 1e3
     tflops = fl / t_launch / 1e12 if fl else None
     gbs = by / t_launch / 1e9 if by else None
@@ -222,6 +226,12 @@ def run_ours(args):
     else:
         roof = {"bound": "tensor", "kernel": cat, "achieved": round(tflops, 2) if tflops else None, "peak": pk["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": round(f_t, 4) if tflops else None, "algorithmic_flops_per_launch": fl}
+    if cat in ("ffn_tail", "dwconv5"):
+        # these kernels are bound by the FP32 FMA pipe of the depthwise 5x5 (25 FMA per hidden element, GELU polynomial not counted):
+        # 148 SMs x 128 FMA/clk at the sampled SM clock
+        fma = N_tok * 360 * 25 / t_launch
+        fma_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6
+        roof["simt_fp32_fma"] = {"achieved_tfma_s": round(fma / 1e12, 2), "peak_tfma_s": round(fma_peak / 1e12, 2), "frac": round(fma / fma_peak, 4)}
     tr = measured_traffic(cat)
     roof["traffic"] = tr.get("bytes_per_launch") if isinstance(tr, dict) else tr
     if isinstance(tr, dict):
