@@ -107,6 +107,13 @@ HITSIR_API int hitsir_forward(HitsirHandle* h, const float* x, float* y, int B, 
 HITSIR_API int hitsir_forward_host(HitsirHandle* h, const float* host_x, float* host_y, int B, int H, int W,
                         float* dev_x, float* dev_y, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The image-file round trip of test_experiment.py:70-77 on the device: `x_hwc` is a PIL-style uint8 image batch [B,H,W,C]
+ * (utils/utils.py:143-145 to_tensor: value / 255), the result is clip(0,1) (experiments/experiment.py:746-748) converted like
+ * torchvision's to_pil_image (value * 255, truncated) into `y_hwc` [B,sH,sW,C].  `dev_x`/`dev_y` are caller-provided fp32 staging
+ * buffers of B*C*H*W and B*C*sH*sW floats; all pointers are device pointers. */
+HITSIR_API int hitsir_forward_u8(HitsirHandle* h, const uint8_t* x_hwc, uint8_t* y_hwc, int B, int H, int W,
+                      float* dev_x, float* dev_y, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Test hook standing in for PyTorch forward hooks on reference sub-modules: the next
  * hitsir_forward copies the named intermediate activation (fp32, NHWC, real channels only) into
  * `dst` (device) and, when `stop` != 0, returns right after producing it.  Names: "shallow",

@@ -984,6 +984,18 @@ HITSIR_API int hitsir_forward_host(HitsirHandle* h, const float* host_x, float* 
   return 0;
 }
 
+HITSIR_API int hitsir_forward_u8(HitsirHandle* h, const uint8_t* x_hwc, uint8_t* y_hwc, int B, int H, int W, float* dev_x, float* dev_y,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  if (!h || !x_hwc || !y_hwc || !dev_x || !dev_y) { set_error("hitsir_forward_u8: null argument"); return HITSIR_ERR_INVALID; }
+  const int s = h->cfg.upscale, ic = h->cfg.in_chans;
+  if (launch_u8hwc_to_f32nchw(x_hwc, dev_x, B, H, W, ic, (cudaStream_t)stream)) return HITSIR_ERR_CUDA;
+  int rc = hitsir_forward(h, dev_x, dev_y, B, H, W, workspace, workspace_bytes, stream);
+  if (rc) return rc;
+  if (launch_f32nchw_to_u8hwc(dev_y, y_hwc, B, H * s, W * s, ic, (cudaStream_t)stream)) return HITSIR_ERR_CUDA;
+  h->launches += 2;
+  return 0;
+}
+
 HITSIR_API int hitsir_set_tap(HitsirHandle* h, const char* name, float* dst, int64_t dst_floats, int stop) {
   if (!h) { set_error("null handle"); return HITSIR_ERR_INVALID; }
   if (!name) { h->tap = Tap(); return 0; }

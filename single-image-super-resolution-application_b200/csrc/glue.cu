@@ -180,6 +180,24 @@ __global__ void upsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__
   }
 }
 
+// PIL-style uint8 HWC image -> [0,1] fp32 NCHW (torchvision to_tensor: true division by 255; reference utils/utils.py:143-145)
+__global__ void u8hwc_to_f32nchw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C) {
+  const long long total = (long long)B * C * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = (int)(i % W); long long t = i / W; const int y = (int)(t % H); t /= H; const int c = (int)(t % C); const int b = (int)(t / C);
+    out[i] = (float)in[(((long long)b * H + y) * W + x) * C + c] / 255.0f;
+  }
+}
+// fp32 NCHW -> clip(0,1) (experiments/experiment.py:746-748, test_experiment.py:75) -> uint8 HWC with to_pil_image's mul(255).byte() truncation
+__global__ void f32nchw_to_u8hwc_kernel(const float* __restrict__ in, uint8_t* __restrict__ out, int B, int H, int W, int C) {
+  const long long total = (long long)B * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C); long long t = i / C; const int x = (int)(t % W); t /= W; const int y = (int)(t % H); const int b = (int)(t / H);
+    const float v = fminf(fmaxf(in[(((long long)b * C + c) * H + y) * W + x], 0.f), 1.f);
+    out[i] = (uint8_t)(v * 255.0f);
+  }
+}
+
 __global__ void fill_kernel(float* p, float v, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -579,6 +597,16 @@ int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, b
 int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st) {
   const long long total = (long long)B * 4 * H * W * (C / 8);
   upsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, out, B, H, W, C);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_u8hwc_to_f32nchw(const uint8_t* in, float* out, int B, int H, int W, int C, cudaStream_t st) {
+  u8hwc_to_f32nchw_kernel<<<grid_for((long long)B * C * H * W, 256), 256, 0, st>>>(in, out, B, H, W, C);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_f32nchw_to_u8hwc(const float* in, uint8_t* out, int B, int H, int W, int C, cudaStream_t st) {
+  f32nchw_to_u8hwc_kernel<<<grid_for((long long)B * C * H * W, 256), 256, 0, st>>>(in, out, B, H, W, C);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

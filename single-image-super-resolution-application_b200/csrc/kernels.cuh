@@ -31,6 +31,9 @@ int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const CUtensorMap& tm_w
 // nearest x2 upsample of an NHWC bf16 map with C channels
 int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st);
 int launch_fill_f32(float* p, float v, long long n, cudaStream_t st);
+// uint8 HWC <-> fp32 NCHW entry / exit (to_tensor: /255; clip(0,1) then to_pil_image: *255 truncated)
+int launch_u8hwc_to_f32nchw(const uint8_t* in, float* out, int B, int H, int W, int C, cudaStream_t st);
+int launch_f32nchw_to_u8hwc(const float* in, uint8_t* out, int B, int H, int W, int C, cudaStream_t st);
 // perm != 0: column c is read from the head-padded position scc_pos(c)
 int launch_f32_to_f32_tap(const void* src, int src_is_bf16, int ld_src, float* dst, long long rows, int cols, int perm, cudaStream_t st);
 // out_bf16[N,192] = bf16(a) (pad 0): GEMM operand shadow of the fp32 stream

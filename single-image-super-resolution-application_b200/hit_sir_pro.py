@@ -437,6 +437,42 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
             self.last_launch_count = int(lib.hitsir_last_launch_count(h))
         return y_host
 
+    def forward_uint8(self, x_u8: torch.Tensor) -> torch.Tensor:
+        """PIL-style images in, PIL-style images out, without leaving the device: `x_u8` (B,H,W,C) uint8 CUDA tensor ->
+        (B, sH, sW, C) uint8 = to_pil_image(model(to_tensor(x)).clip(0, 1)) of test_experiment.py:70-77 (utils/utils.py:143-145,
+        experiments/experiment.py:746-748).  The D2H copy of the result is 4x smaller than the fp32 NCHW output."""
+        if x_u8.device.type != "cuda" or x_u8.dtype != torch.uint8 or x_u8.dim() != 4:
+            raise RuntimeError("forward_uint8 expects a (B,H,W,C) uint8 CUDA tensor: there is no CPU path.")
+        B, H, W, C = x_u8.shape
+        if C != self.in_chans:
+            raise RuntimeError(f"expected {self.in_chans} channels, got {C}")
+        device = x_u8.device
+        x_u8 = x_u8.contiguous()
+        y = torch.empty((B, H * self.upscale, W * self.upscale, C), dtype=torch.uint8, device=device)
+        lib = _capi.load()
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            h = self._handle(device)
+            self._sync_weights(h, device, stream)
+            ws = self._workspace(h, device, B, H, W)
+            base = (ws.data_ptr() + 255) // 256 * 256
+            dx = torch.empty((B, C, H, W), dtype=torch.float32, device=device)
+            dy = torch.empty((B, C, H * self.upscale, W * self.upscale), dtype=torch.float32, device=device)
+            _capi.check(lib.hitsir_forward_u8(h, ctypes.c_void_p(x_u8.data_ptr()), ctypes.c_void_p(y.data_ptr()), B, H, W,
+                                              ctypes.c_void_p(dx.data_ptr()), ctypes.c_void_p(dy.data_ptr()),
+                                              ctypes.c_void_p(base), ws.numel() - (base - ws.data_ptr()), ctypes.c_void_p(stream)))
+            self.last_launch_count = int(lib.hitsir_last_launch_count(h))
+        return y
+
+    def load_checkpoint(self, path_or_dict, map_location="cpu") -> Optional[int]:
+        """Load a checkpoint written by the reference harness (experiments/experiment.py:257-263: {'start_epoch', 'model',
+        'optimizer'}; read back at :222-223 and test_experiment.py:43-44) or a bare state_dict, strictly.  Returns
+        'start_epoch' when present."""
+        ck = path_or_dict if isinstance(path_or_dict, dict) else torch.load(path_or_dict, map_location=map_location, weights_only=True)
+        sd = ck["model"] if isinstance(ck, dict) and "model" in ck and isinstance(ck["model"], dict) else ck
+        self.load_state_dict(sd, strict=True)
+        return ck.get("start_epoch") if isinstance(ck, dict) and "start_epoch" in ck else None
+
     def __del__(self):
         try:
             lib = _capi.load()

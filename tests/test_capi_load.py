@@ -60,3 +60,21 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "oracle" not in src.replace("oracle tap", ""), os.path.join(dirpath, f)
+
+
+def test_load_checkpoint_in_reference_format(tmp_path):
+    """experiments/experiment.py:257-263 writes {'start_epoch', 'model', 'optimizer'}; :222-223 / test_experiment.py:43-44 read it."""
+    kw = dict(hitsir_b200.PRO_KWARGS)
+    kw.update(depths=[2], num_heads=[6])
+    src = hitsir_b200.HiT_SIR(True, True, True, **kw)
+    sd = {k: torch.randn_like(v) for k, v in src.state_dict().items()}
+    path = tmp_path / "new_epoch_model.pth"
+    torch.save({"start_epoch": 17, "model": sd, "optimizer": {"state": {}, "param_groups": []}}, path)
+    dst = hitsir_b200.HiT_SIR(True, True, True, **kw)
+    assert dst.load_checkpoint(str(path)) == 17
+    for k, v in dst.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+    assert dst.load_checkpoint(sd) is None                       # a bare state_dict works too
+    bad = dict(sd); bad.pop(next(iter(bad)))
+    with pytest.raises(RuntimeError):                            # strict, like the reference's load_state_dict
+        dst.load_checkpoint({"model": bad})

@@ -179,3 +179,23 @@ def test_host_pipeline_matches_forward():
     pipe.wait()
     for y, o in zip(ys, outs):
         assert torch.equal(y, o)
+
+
+def test_forward_uint8_matches_float_pipeline_bit_exactly():
+    """uint8 HWC in / out on the device == to_pil_image(model(to_tensor(x)).clip(0, 1)) of test_experiment.py:70-77:
+    division by 255, clip, multiplication by 255 and truncation are integer/byte work -> bit-exact against our own float path,
+    and within one grey level of the fp32 oracle."""
+    model, oracle = build_pair((1, 1, 1), "nearest+conv", 4, "init", 121)
+    g = torch.Generator().manual_seed(5)
+    x_u8 = torch.randint(0, 256, (2, 40, 44, 3), dtype=torch.uint8, generator=g)
+    model = model.to(DEV)
+    with torch.no_grad():
+        y_u8 = model.forward_uint8(x_u8.to(DEV)).cpu()
+        x_f = (x_u8.permute(0, 3, 1, 2).float() / 255.0).contiguous()
+        y_f = model(x_f.to(DEV)).cpu()
+        ref = oracle(x_f)
+    expect = (y_f.clip(0, 1) * 255.0).to(torch.uint8).permute(0, 2, 3, 1)
+    assert y_u8.shape == (2, 160, 176, 3) and y_u8.dtype == torch.uint8
+    assert torch.equal(y_u8, expect)
+    ref_u8 = (ref.clip(0, 1) * 255.0).to(torch.uint8).permute(0, 2, 3, 1)
+    assert (y_u8.int() - ref_u8.int()).abs().max().item() <= 1
