@@ -1,6 +1,6 @@
 """Benchmark of the HiT-SIR-pro forward pass (BASELINE.json metric: output megapixels/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg4|cfg5|cfg1]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg5|cfg1]
 
 One step = one forward of one batch of synthetic LR images through the public nn.Module (-> C ABI -> CUDA).
 N=1 workload: BASELINE.json configs[1] (32 x 3 x 256 x 256 LR, x4 'nearest+conv', pro config).  For N>1 the
@@ -24,12 +24,13 @@ WORKLOADS = {
     # name: (flags, upsampler, upscale, batch, H, W, description)
     "cfg1": ((1, 1, 1), "nearest+conv", 4, 1, 64, 64, "HiT-SIR-pro x4, 1x 64x64 LR"),
     "cfg2": ((1, 1, 1), "nearest+conv", 4, 32, 256, 256, "HiT-SIR-pro x4 batched inference, 32x 256x256 LR"),
+    "cfg3": ((1, 1, 1), "pixelshuffle", 2, 8, 576, 576, "HiT-SIR-pro x2, the 8 halo tiles (576x576) of a 1920x1080 frame as one batch (tile t -> rank t % N)"),
     "cfg4": ((1, 1, 1), "nearest+conv", 4, 16, 512, 512, "hitsir_pro_gan generator x4, 16x 512x512 LR"),
     "cfg5": ((0, 0, 0), "nearest+conv", 4, 32, 256, 256, "ablation HiT-SIR-pro x4 casa=False mulsizeconvextract=False, 32x 256x256 LR"),
 }
 # algorithmic GFLOP per image of the reference formulation (conv+GEMM+bmm, FMA=2; torch.utils.flop_counter on the
 # reference module)
-GFLOP_PER_IMAGE = {"cfg1": 101.81, "cfg2": 1575.8, "cfg4": 6260.6, "cfg5": 1417.1}
+GFLOP_PER_IMAGE = {"cfg1": 101.81, "cfg2": 1575.8, "cfg3": 7110.2, "cfg4": 6260.6, "cfg5": 1417.1}
 
 
 def peaks():
