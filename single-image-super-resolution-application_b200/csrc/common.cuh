@@ -23,6 +23,20 @@ typedef __nv_bfloat16 bf16;
 
 void set_error(const char* fmt, ...);
 
+// Opt a kernel in to its dynamic shared-memory size once per (kernel, device): the attribute is per device, and a process may
+// drive several (the per-call `mask` static lives at the call site, one per kernel instantiation).
+template <class Kernel>
+static inline int ensure_dynamic_smem(Kernel kernel, int bytes, unsigned long long* mask) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { set_error("cudaGetDevice failed"); return 1; }
+  const unsigned long long bit = 1ull << (dev & 63);
+  if (*mask & bit) return 0;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize=%d) -> %s", bytes, cudaGetErrorString(e)); return 1; }
+  *mask |= bit;
+  return 0;
+}
+
 static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return cdiv(a, b) * b; }

@@ -198,11 +198,8 @@ conv3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 template <int BN>
 int launch_bn(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, int num_sms, cudaStream_t st) {
   using C = Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    HITSIR_CHECK(cudaFuncSetAttribute(conv3_c64_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(conv3_c64_kernel<BN>, C::kSmemBytes, &configured)) return 1;
   const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
   if (grid <= 0) return 0;
   conv3_c64_kernel<BN><<<grid, 384, C::kSmemBytes, st>>>(ta, tb, to, p);

@@ -414,11 +414,8 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
 // h1: bf16 [B,H,W,384]; fc2 packed weights tensor map (box {64, 192}); x: fp32 residual stream [B,H,W,180], updated in place
 int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
                     const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    HITSIR_CHECK(cudaFuncSetAttribute(ffn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(ffn_tail_kernel, kSmemBytes, &configured)) return 1;
   Params p;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 7) / 8;

@@ -578,12 +578,9 @@ int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* 
   return 0;
 }
 int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, bf16* h2, int B, int H, int W, int num_sms, cudaStream_t st) {
-  static bool configured = false;
   const int smem = 2 * kDwTileBytes + 32;
-  if (!configured) {
-    HITSIR_CHECK(cudaFuncSetAttribute(dwconv5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(dwconv5_kernel, smem, &configured)) return 1;
   CUtensorMap tm;
   if (make_tmap_nhwc_plain(&tm, h1, B, H, W, kHidp, 64, kDwPW, kDwPH)) return 1;
   const int tiles_x = (W + kDwTW - 1) / kDwTW, tiles_y = (H + kDwTH - 1) / kDwTH;

@@ -417,11 +417,8 @@ scc_dense_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant
 
 template <int LT>
 int launch_lt(const CUtensorMap& tm_t, const CUtensorMap& tm_o, const Params& p, int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    HITSIR_CHECK(cudaFuncSetAttribute(scc_dense_kernel<LT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(scc_dense_kernel<LT>, kSmemBytes, &configured)) return 1;
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;
   scc_dense_kernel<LT><<<grid, 384, kSmemBytes, st>>>(tm_t, tm_o, p);
   HITSIR_CHECK(cudaGetLastError());

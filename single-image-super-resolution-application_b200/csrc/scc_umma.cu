@@ -604,11 +604,8 @@ int launch_scc_images(const SccW& w, int win, int base, uint8_t* pool_img, uint8
 }
 
 int launch_scc_umma(const bf16* t, const SccGeom& g, const SccW& w, bf16* out, float* dbg, int num_sms, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    HITSIR_CHECK(cudaFuncSetAttribute(scc_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(scc_umma_kernel, kSmemBytes, &configured)) return 1;
   const SccTile tg = scc_tile(g.w);
   if (tg.TT == 0) { set_error("launch_scc_umma: unsupported window %d", g.w); return 1; }
   Params p;

@@ -259,11 +259,8 @@ int make_tmap_nhwc_plain(CUtensorMap* m, const void* base, int B, int H, int W, 
 template <int BN>
 static int launch_bn(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb, int num_sms, cudaStream_t st) {
   using Cfg = UmmaCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    HITSIR_CHECK(cudaFuncSetAttribute(umma_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(umma_gemm_kernel<BN>, Cfg::kSmemBytes, &configured)) return 1;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   if (grid <= 0) return 0;

@@ -412,11 +412,8 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 template <int BN, int EQ>
 static int launch_tma_bn(const GemmParams& p, const CUtensorMap* maps, int num_sms, cudaStream_t st) {
   using Cfg = TmaCfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    HITSIR_CHECK(cudaFuncSetAttribute(umma_gemm_tma_kernel<BN, EQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    configured = true;
-  }
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(umma_gemm_tma_kernel<BN, EQ>, Cfg::kSmemBytes, &configured)) return 1;
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   if (grid <= 0) return 0;
