@@ -61,25 +61,21 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
-// Packed-fp32 GELU for two values: x * Phi(x) with Phi(x) = 0.5 + xc * Q(xc^2), xc = clamp(x, +-3*sqrt(2)), Q a degree-9 minimax fit of
-// 0.5*erf(x/sqrt2)/x rescaled so that Phi saturates at exactly 0 / 1.  |error| <= 2.2e-5 * max(|x|, 1) (fp32 Horner noise included), an order
-// of magnitude below the bf16 rounding of the stored value; no MUFU, 16 issue slots per pair (FFMA2/FMUL2) instead of ~70 for two erff().
+// Packed-fp32 GELU (erf form, /root/reference/models/hit_sir_pro.py:32 nn.GELU) for two values: x * Phi(x) with
+// Phi(x) ~= 1 / (1 + 2^(-x (a + b s + c s^2))), s = min(x^2, 81): a minimax fit of the normal CDF by a logistic of an odd quintic.
+// |error| <= 1.6e-5 * max(|x|, 1) (fp32 evaluation and ex2.approx / rcp.approx included), two orders of magnitude below the bf16 rounding of
+// the stored value.  6 packed FMA-pipe instructions + 2 FMNMX + 4 MUFU per pair (the polynomial-only form needed 12 + 4 FMNMX: the FMA pipe
+// is the binding resource of the FFN kernels, the MUFU pipe is otherwise idle).  Saturates exactly: 2^z -> inf gives 0, 2^z -> 0 gives x.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float2 gelu2(float2 x) {
-  const float X = 4.242640687f;
-  const float2 xc = make_float2(fminf(fmaxf(x.x, -X), X), fminf(fmaxf(x.y, -X), X));
-  const float2 s = __fmul2_rn(xc, xc);
-  float2 p = make_float2(-3.086732500e-12f, -3.086732500e-12f);
-  p = __ffma2_rn(p, s, make_float2(3.179519986e-10f, 3.179519986e-10f));
-  p = __ffma2_rn(p, s, make_float2(-1.470231326e-08f, -1.470231326e-08f));
-  p = __ffma2_rn(p, s, make_float2(4.085154930e-07f, 4.085154930e-07f));
-  p = __ffma2_rn(p, s, make_float2(-7.745199668e-06f, -7.745199668e-06f));
-  p = __ffma2_rn(p, s, make_float2(1.082166939e-04f, 1.082166939e-04f));
-  p = __ffma2_rn(p, s, make_float2(-1.169120996e-03f, -1.169120996e-03f));
-  p = __ffma2_rn(p, s, make_float2(9.949907623e-03f, 9.949907623e-03f));
-  p = __ffma2_rn(p, s, make_float2(-6.647990253e-02f, -6.647990253e-02f));
-  p = __ffma2_rn(p, s, make_float2(3.989525639e-01f, 3.989525639e-01f));
-  const float2 phi = __ffma2_rn(xc, p, make_float2(0.5f, 0.5f));
-  return __fmul2_rn(x, phi);
+  float2 s = __fmul2_rn(x, x);
+  s.x = fminf(s.x, 81.f); s.y = fminf(s.y, 81.f);          // the quintic turns over at |x| ~ 11.4; beyond 9 the logistic is saturated anyway
+  float2 p = __ffma2_rn(s, make_float2(9.481962249e-04f, 9.481962249e-04f), make_float2(-1.064097551e-01f, -1.064097551e-01f));
+  p = __ffma2_rn(p, s, make_float2(-2.301458255f, -2.301458255f));
+  const float2 z = __fmul2_rn(p, x);
+  const float2 e = __fadd2_rn(make_float2(ex2_approx(z.x), ex2_approx(z.y)), make_float2(1.f, 1.f));
+  return __fmul2_rn(x, make_float2(rcp_approx(e.x), rcp_approx(e.y)));
 }
 
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
@@ -92,6 +88,14 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
+}
+// bf16 pair -> fp32 pair with two byte permutes: keeps the conversion on the ALU pipe (the compiler's own choice puts every other one on
+// the FMA pipe as IMAD.U32 x 65536, which is the saturated pipe of the depthwise-conv loops)
+__device__ __forceinline__ float2 unpack_bf16x2_alu(uint32_t u) {
+  uint32_t lo, hi;
+  asm("prmt.b32 %0, %1, 0, 0x1044;" : "=r"(lo) : "r"(u));
+  asm("prmt.b32 %0, %1, 0, 0x3244;" : "=r"(hi) : "r"(u));
+  return make_float2(__uint_as_float(lo), __uint_as_float(hi));
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

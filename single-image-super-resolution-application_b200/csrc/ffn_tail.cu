@@ -263,63 +263,14 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
       p.cavg[pix] = ls * (1.0f / (float)kC);
       p.cmax[pix] = lm;
     };
-    int it = 0, tprev = -1;
-    for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
-      // ---------- depthwise 5x5 + GELU + input on this half's three slices -> A operand
-#pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
-        const int k = half + 2 * j;
-        const uint32_t u = (uint32_t)(it * 3 + j);
-        const int c = k * 64 + 2 * lane;
-        const bool live = c < kHid;
-        mbar_wait(halo_full(half), u & 1u);
-        const float2 bs = wtab[25 * 32];
-        float2 acc[4][4];
-#pragma unroll
-        for (int oy = 0; oy < 4; ++oy)
-#pragma unroll
-          for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = bs;
-        uint32_t center[4][4];
-        const uint32_t* tp0 = halo + (by * kPW + bx) * 32;
-#pragma unroll
-        for (int iy = 0; iy < 8; ++iy) {
-          float2 in[8];
-#pragma unroll
-          for (int ix = 0; ix < 8; ++ix) {
-            const uint32_t v = tp0[(iy * kPW + ix) * 32];
-            in[ix] = unpack_bf16x2(v);
-            if (iy >= 2 && iy < 6 && ix >= 2 && ix < 6) center[iy - 2][ix - 2] = v;
-          }
-#pragma unroll
-          for (int ky = 0; ky < 5; ++ky) {
-            const int oy = iy - ky;                        // compile-time after unrolling
-            if (oy >= 0 && oy < 4) {
-#pragma unroll
-              for (int ox = 0; ox < 4; ++ox)
-#pragma unroll
-                for (int kx = 0; kx < 5; ++kx) acc[oy][ox] = __ffma2_rn(in[ox + kx], wtab[(ky * 5 + kx) * 32], acc[oy][ox]);
-            }
-          }
-        }
-        mbar_arrive_warp(halo_empty(half));                // every input word of this warp is in registers
-        mbar_wait(a_empty(half), (u & 1u) ^ 1u);           // the MMAs of the previous use of this A buffer are done
-#pragma unroll
-        for (int oy = 0; oy < 4; ++oy) {
-#pragma unroll
-          for (int ox = 0; ox < 4; ++ox) {
-            const float2 cv = unpack_bf16x2(center[oy][ox]);
-            const float2 g = gelu2(acc[oy][ox]);
-            const uint32_t o = live ? pack_bf16x2(cv.x + g.x, cv.y + g.y) : 0u;
-            const int row = (by + oy) * 16 + bx + ox;      // A row = pixel of the 8 x 16 tile
-            *reinterpret_cast<uint32_t*>(abuf + row * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(row & 7)) << 4) + (lane & 3) * 4) = o;
-          }
-        }
-        fence_proxy_async_smem();
-        mbar_arrive_warp(a_full(half));
-      }
-      // ---------- epilogue: x = x + LayerNorm(acc + b2) over the 180 real columns, 16-column slices
-      const int as = it & 1;
-      mbar_wait(d_full(as), ((uint32_t)(it >> 1)) & 1u);
+    // ---------- epilogue of one finished tile (iteration index e): x = x + LayerNorm(acc + b2) over the 180 real columns.  It is cut
+    // into a statistics pass (epi_begin) and three 64-column groups (epi_group) so that the main loop can interleave it with the conv
+    // slices of the NEXT tile: the residual boxes of group g + 1 then have a whole conv slice to be stored, drained and re-loaded, the
+    // last fc2 MMA has long retired when its accumulator is read, and the halo load of the next slice hides under epilogue work.
+    float e_mean = 0.f, e_rstd = 0.f, e_ls = 0.f, e_lm = -INFINITY;
+    auto epi_begin = [&](int e, int tflush) {
+      const int as = e & 1;
+      mbar_wait(d_full(as), ((uint32_t)(e >> 1)) & 1u);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 192);
       // LayerNorm statistics without cancellation: per 16-column group (mean, M2) from registers, merged with Chan's parallel update
@@ -352,11 +303,10 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
           n = nn;
         }
       }
-      float2* part = s_part + (it & 1) * 512;
+      float2* part = s_part + (e & 1) * 512;
       part[hs * 128 + r] = make_float2(mean, m2);
       epi_bar_sync();
-      if (want_stats && tprev >= 0) flush_pixel_stats(tprev, it - 1);
-      tprev = t;
+      if (want_stats && tflush >= 0) flush_pixel_stats(tflush, e - 1);
 #pragma unroll
       for (int o = 1; o < 4; ++o) {
         const int ho = (hs + o) & 3;
@@ -367,37 +317,108 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         m2 += tv.y + d * d * (n * cnt / nn);
         n = nn;
       }
-      const float rstd = rsqrtf(m2 * (1.0f / (float)kC) + 1e-5f);
-      float ls = 0.f, lm = -INFINITY;                       // channel sum / max of this thread's real output columns
+      e_mean = mean;
+      e_rstd = rsqrtf(m2 * (1.0f / (float)kC) + 1e-5f);
+      e_ls = 0.f; e_lm = -INFINITY;                         // channel sum / max of this thread's real output columns
+    };
+    auto epi_group = [&](int e, int g) {
+      const int as = e & 1;
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 192);
+      const int c0 = 64 * g + 16 * hs;
+      float v[16];
+      tmem_ld16(tacc + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaf((v[i] + s_bias[c0 + i] - e_mean) * e_rstd, s_gamma[c0 + i], s_beta[c0 + i]);   // gamma = beta = 0 beyond 180
+      const uint32_t ub = (uint32_t)e * 6u + (uint32_t)(2 * g + (hs >> 1));
+      const int bb = (int)(ub % kNBox);
+      mbar_wait(in_bar(bb), (ub / kNBox) & 1u);
+      uint8_t* fb = row_ptr + bb * kBoxBytes;
+      const uint32_t ch0 = (uint32_t)((hs & 1) * 4);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        float4* ptr = reinterpret_cast<float4*>(fb + (((ch0 + (uint32_t)ch) ^ rsw) << 4));
+        const float4 rr = *ptr;
+        const float4 o = make_float4(v[4 * ch] + rr.x, v[4 * ch + 1] + rr.y, v[4 * ch + 2] + rr.z, v[4 * ch + 3] + rr.w);
+        *ptr = o;
+        if (c0 + 4 * ch < kC) {                             // 180 = 45 chunks of 4: a chunk is entirely real or entirely padding
+          e_ls += (o.x + o.y) + (o.z + o.w);
+          e_lm = fmaxf(e_lm, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+        }
+      }
+      fence_proxy_async_smem();
+      mbar_arrive_warp(out_bar(bb));
+      if (g == 2) {
+        tc_fence_before();
+        mbar_arrive_warp(d_empty(as));
+        if (want_stats) s_part2[(e & 1) * 512 + hs * 128 + r] = make_float2(e_ls, e_lm);   // flushed after the next tile's LayerNorm barrier
+      }
+    };
+    int it = 0, tprev = -1, tpp = -1;
+    for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
+      // ---------- depthwise 5x5 + GELU + input on this half's three slices -> A operand; after slice j, group j of the previous tile's epilogue
 #pragma unroll 1
-      for (int g = 0; g < 3; ++g) {
-        const int c0 = 64 * g + 16 * hs;
-        float v[16];
-        tmem_ld16(tacc + c0, v);
+      for (int j = 0; j < 3; ++j) {
+        const int k = half + 2 * j;
+        const uint32_t u = (uint32_t)(it * 3 + j);
+        const int c = k * 64 + 2 * lane;
+        const bool live = c < kHid;
+        mbar_wait(halo_full(half), u & 1u);
+        const float2 bs = wtab[25 * 32];
+        float2 acc[4][4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = fmaf((v[i] + s_bias[c0 + i] - mean) * rstd, s_gamma[c0 + i], s_beta[c0 + i]);   // gamma = beta = 0 beyond 180
-        const uint32_t ub = (uint32_t)it * 6u + (uint32_t)(2 * g + (hs >> 1));
-        const int bb = (int)(ub % kNBox);
-        mbar_wait(in_bar(bb), (ub / kNBox) & 1u);
-        uint8_t* fb = row_ptr + bb * kBoxBytes;
-        const uint32_t ch0 = (uint32_t)((hs & 1) * 4);
+        for (int oy = 0; oy < 4; ++oy)
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          float4* ptr = reinterpret_cast<float4*>(fb + (((ch0 + (uint32_t)ch) ^ rsw) << 4));
-          const float4 rr = *ptr;
-          const float4 o = make_float4(v[4 * ch] + rr.x, v[4 * ch + 1] + rr.y, v[4 * ch + 2] + rr.z, v[4 * ch + 3] + rr.w);
-          *ptr = o;
-          if (c0 + 4 * ch < kC) {                           // 180 = 45 chunks of 4: a chunk is entirely real or entirely padding
-            ls += (o.x + o.y) + (o.z + o.w);
-            lm = fmaxf(lm, fmaxf(fmaxf(o.x, o.y), fmaxf(o.z, o.w)));
+          for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = bs;
+        uint32_t center[4][4];
+        const uint32_t* tp0 = halo + (by * kPW + bx) * 32;
+#pragma unroll
+        for (int iy = 0; iy < 8; ++iy) {
+          float2 in[8];
+#pragma unroll
+          for (int ix = 0; ix < 8; ++ix) {
+            const uint32_t v = tp0[(iy * kPW + ix) * 32];
+            in[ix] = unpack_bf16x2_alu(v);
+            if (iy >= 2 && iy < 6 && ix >= 2 && ix < 6) center[iy - 2][ix - 2] = v;
+          }
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky) {
+            const int oy = iy - ky;                        // compile-time after unrolling
+            if (oy >= 0 && oy < 4) {                        // runs of four FFMA2 share the tap: the multiplier comes from the operand-reuse cache
+#pragma unroll
+              for (int kx = 0; kx < 5; ++kx) {
+                const float2 wt = wtab[(ky * 5 + kx) * 32];
+#pragma unroll
+                for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = __ffma2_rn(in[ox + kx], wt, acc[oy][ox]);
+              }
+            }
+          }
+        }
+        mbar_arrive_warp(halo_empty(half));                // every input word of this warp is in registers
+        mbar_wait(a_empty(half), (u & 1u) ^ 1u);           // the MMAs of the previous use of this A buffer are done
+#pragma unroll
+        for (int oy = 0; oy < 4; ++oy) {
+#pragma unroll
+          for (int ox = 0; ox < 4; ++ox) {
+            const float2 cv = unpack_bf16x2_alu(center[oy][ox]);
+            const float2 g = gelu2(acc[oy][ox]);
+            const float2 h2 = __fadd2_rn(cv, g);
+            const uint32_t o = live ? pack_bf16x2(h2.x, h2.y) : 0u;
+            const int row = (by + oy) * 16 + bx + ox;      // A row = pixel of the 8 x 16 tile
+            *reinterpret_cast<uint32_t*>(abuf + row * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(row & 7)) << 4) + (lane & 3) * 4) = o;
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive_warp(out_bar(bb));
+        mbar_arrive_warp(a_full(half));
+        if (it > 0) {
+          if (j == 0) epi_begin(it - 1, tpp);
+          epi_group(it - 1, j);
+        }
       }
-      tc_fence_before();
-      mbar_arrive_warp(d_empty(as));
-      if (want_stats) s_part2[(it & 1) * 512 + hs * 128 + r] = make_float2(ls, lm);   // flushed after the next tile's LayerNorm barrier
+      tpp = tprev; tprev = t;
+    }
+    if (it > 0) {                                           // the last tile's epilogue has nothing to hide behind
+      epi_begin(it - 1, tpp);
+      for (int g = 0; g < 3; ++g) epi_group(it - 1, g);
     }
     if (want_stats && tprev >= 0) { epi_bar_sync(); flush_pixel_stats(tprev, it - 1); }
   }
