@@ -43,6 +43,7 @@ struct BlockW {
   const float *g1, *b1, *g2, *b2;
   CasaW casa;
   float *casa_w1 = nullptr, *casa_w2 = nullptr;
+  uint32_t* casa_bfrag = nullptr;
   SccW scc;
   float* bias_tbl = nullptr;
   uint8_t *pool_img = nullptr, *bias_img = nullptr, *w_img = nullptr;
@@ -359,6 +360,10 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
         bw.casa.l1s_w = P(h, q + ".linear1_second.weight"); bw.casa.l1s_b = P(h, q + ".linear1_second.bias");
         bw.casa.l2f_w = P(h, q + ".linear2_first.weight"); bw.casa.l2f_b = P(h, q + ".linear2_first.bias");
         bw.casa.l2s_w = P(h, q + ".linear2_second.weight"); bw.casa.l2s_b = P(h, q + ".linear2_second.bias");
+        bw.casa.bfrag = nullptr;
+        if (dev_alloc(h, &bw.casa_bfrag, (size_t)casa_bfrag_words())) return 1;
+        if (launch_pack_casa_bfrag(bw.casa, bw.casa_bfrag, st)) return 1;
+        bw.casa.bfrag = bw.casa_bfrag;
       }
       const std::string s = p + ".correlation";
       bw.scc.wk1 = P(h, s + ".k_generate1.weight"); bw.scc.bk1 = P(h, s + ".k_generate1.bias");

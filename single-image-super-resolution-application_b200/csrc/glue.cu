@@ -2,6 +2,9 @@
 // contraction or the window self-correlation): entry im2col, LayerNorm, depthwise 5x5 + GELU,
 // casa (SpatialChannelAttention) statistics and gating, UnionAttention/Fusion statistics and
 // gating, nearest upsampling.  Token-major (NHWC) throughout; 128-bit accesses where rows allow.
+#include <cstdlib>
+#include <cstring>
+
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -416,6 +419,176 @@ __global__ void __launch_bounds__(96, 10) qkv_casa_kernel(const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// casa gate on the tensor core.  The two Conv2d(1, C, 3) of SpatialChannelAttention (:345-347) are a K = 9 contraction per pixel
+// and channel: 18 FP32 FMAs per output on the SIMT path above, which made the kernel FMA/issue-bound at 2.8 TB/s.  Here they are
+// warp-level bf16 MMAs (m16n8k16, fp32 accumulate) with a three-term split so that nothing is lost to bf16:
+//     k  0.. 8: a_hi[tap] * W_hi[tap]      k  9..17: a_lo[tap] * W_hi[tap]      k 18..26: a_hi[tap] * W_lo[tap]
+//     k 27, 28: 1 * b_hi, 1 * b_lo         k 29..31: 0                          (x = x_hi + x_lo, both bf16: ~16 mantissa bits)
+// CTA = (image, padded row), 4 warps, 5 CTAs per SM; per run of 32 padded pixels: the token rows are staged with cp.async (16-byte chunks through the
+// reflect map), every warp owns 6 n-tiles (48 head-padded positions) whose B fragments stay in registers for the whole row, the A
+// rows [32 px][32 k] of both statistic maps are built once per run in shared memory, and the gated bf16 tokens leave through a
+// padded shared tile as whole 16-byte chunks.  What is left per output: 2 LeakyReLU, 2 FMA, the token read and the bf16 pack.
+constexpr int kMmaRun = 32;
+constexpr int kMmaXS = 184;                      // staged token row: 180 fp32 + 4 (row = 736 B, a multiple of 16)
+constexpr int kMmaOS = 100;                      // output row: 96 words + 4 (rows of a quad-store land on distinct banks)
+constexpr int kMmaAS = 20;                       // A row: 16 words + 4
+constexpr int kMmaSmem = kMmaRun * kMmaXS * 4 + kMmaRun * kMmaOS * 4 + 2 * kMmaRun * kMmaAS * 4 + 2 * kCp * 4 + 2 * 3 * (kMmaRun + 2) * 4;
+constexpr int kCasaBfragWords = 24 * 2 * 2 * 2 * 32;
+
+__device__ __forceinline__ void split_bf16(float v, uint16_t* hi, uint16_t* lo) {
+  const bf16 h = __float2bfloat16_rn(v);
+  const bf16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+  *hi = *reinterpret_cast<const uint16_t*>(&h); *lo = *reinterpret_cast<const uint16_t*>(&l);
+}
+__device__ __forceinline__ void mma_bf16_16816(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// B fragments of both 3x3 filters in the k order above: img[n-tile 24][conv 2][k-step 2][reg 2][lane 32]
+__global__ void casa_bfrag_kernel(CasaW w, uint32_t* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= kCasaBfragWords) return;
+  const int lane = idx & 31, i = (idx >> 5) & 1, s = (idx >> 6) & 1, v = (idx >> 7) & 1, nt = idx >> 8;
+  const int c = scc_chan(nt * 8 + (lane >> 2));
+  const float* wt = v == 0 ? w.w1 : w.w2;
+  const float* bs = v == 0 ? w.b1 : w.b2;
+  uint16_t out[2];
+#pragma unroll
+  for (int e = 0; e < 2; ++e) {
+    const int k = s * 16 + i * 8 + (lane & 3) * 2 + e;
+    uint16_t hi = 0, lo = 0, r = 0;
+    if (c >= 0) {
+      if (k < 27) { split_bf16(wt[(k % 9) * kC + c], &hi, &lo); r = k < 18 ? hi : lo; }
+      else if (k < 29) { split_bf16(bs[c], &hi, &lo); r = k == 27 ? hi : lo; }
+    }
+    out[e] = r;
+  }
+  img[idx] = (uint32_t)out[0] | ((uint32_t)out[1] << 16);
+}
+
+__global__ void __launch_bounds__(128) qkv_casa_mma_kernel(const float* __restrict__ x, PadGeom g, const float* __restrict__ cavg,
+                                                           const float* __restrict__ cmax, const float* __restrict__ s1, const float* __restrict__ s2,
+                                                           const uint32_t* __restrict__ bfrag, bf16* __restrict__ t) {
+  extern __shared__ __align__(16) uint8_t smem_casa[];
+  float* xs = reinterpret_cast<float*>(smem_casa);                       // [run][184]
+  uint32_t* os = reinterpret_cast<uint32_t*>(xs + kMmaRun * kMmaXS);     // [run][100]
+  uint32_t* as = os + kMmaRun * kMmaOS;                                  // [2][run][20]
+  float* gs = reinterpret_cast<float*>(as + 2 * kMmaRun * kMmaAS);       // [2][192]: 0.5 * channel gate in head-padded order (0 on pads)
+  float* sw = gs + 2 * kCp;                                              // [2][3][run + 2] statistic windows
+  const int yp = blockIdx.x % g.Hp, b = blockIdx.x / g.Hp;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, gq = lane >> 2, tq = lane & 3;
+  const int ysrc = reflect_src(yp, g.H);
+  const float* xrow = x + ((long long)b * g.H + ysrc) * g.W * kC;
+  const float* ca = cavg + (long long)b * g.H * g.W;
+  const float* cm = cmax + (long long)b * g.H * g.W;
+  const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs);
+  auto stage_x = [&](int xs0) {
+    const int n = min(kMmaRun, g.Wp - xs0);
+    for (int q = tid; q < n * 45; q += 128) {
+      const int px = q / 45, ch = q - px * 45;
+      const float* src = xrow + (long long)reflect_src(xs0 + px, g.W) * kC + ch * 4;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xs_addr + (uint32_t)(px * kMmaXS + ch * 4) * 4u), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_x(0);
+  // B fragments of this warp's six n-tiles and the per-column constants
+  uint32_t bf[6][2][2][2];
+  int cA[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int nt = warp * 6 + j;
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int s = 0; s < 2; ++s)
+#pragma unroll
+        for (int i = 0; i < 2; ++i) bf[j][v][s][i] = bfrag[((((nt * 2 + v) * 2 + s) * 2 + i) << 5) + lane];
+    cA[j] = scc_chan(nt * 8 + tq * 2);                   // an even position is never a pad
+  }
+  for (int i = tid; i < 2 * kCp; i += 128) {
+    const int v = i / kCp, pos = i - v * kCp, c = scc_chan(pos);
+    gs[i] = c >= 0 ? 0.5f * (v == 0 ? s1 : s2)[(long long)b * kC + c] : 0.f;
+  }
+  bf16* trow0 = t + ((long long)b * g.Hp + yp) * g.Wp * kCp;
+  for (int xs0 = 0; xs0 < g.Wp; xs0 += kMmaRun) {
+    const int n = min(kMmaRun, g.Wp - xs0);
+    // statistic windows (zero padding of the PADDED map, values gathered through the reflect map)
+    for (int i = tid; i < 2 * 3 * (kMmaRun + 2); i += 128) {
+      const int v = i / (3 * (kMmaRun + 2)), r2 = i - v * 3 * (kMmaRun + 2);
+      const int rr = r2 / (kMmaRun + 2), cc = r2 - rr * (kMmaRun + 2);
+      const int yy = yp + rr - 1, xx = xs0 + cc - 1;
+      const bool ok = yy >= 0 && yy < g.Hp && xx >= 0 && xx < g.Wp;
+      const int src = ok ? reflect_src(yy, g.H) * g.W + reflect_src(xx, g.W) : 0;
+      sw[i] = ok ? (v == 0 ? ca : cm)[src] : 0.f;
+    }
+    __syncthreads();                                       // windows written; the previous run's output tile has been copied out
+    {                                                      // A rows: thread = (map v, pixel)
+      const int v = tid / kMmaRun, px = tid % kMmaRun;
+      if (v < 2) {
+      const float* wv = sw + v * 3 * (kMmaRun + 2);
+      uint16_t hi[9], lo[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) split_bf16(wv[(tap / 3) * (kMmaRun + 2) + px + (tap % 3)], &hi[tap], &lo[tap]);
+      uint16_t row[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) row[k] = k < 9 ? hi[k] : k < 18 ? lo[k - 9] : k < 27 ? hi[k - 18] : k < 29 ? (uint16_t)0x3f80 : (uint16_t)0;
+      uint4* dst = reinterpret_cast<uint4*>(as + (v * kMmaRun + px) * kMmaAS);
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4)
+        dst[c4] = make_uint4((uint32_t)row[8 * c4] | ((uint32_t)row[8 * c4 + 1] << 16), (uint32_t)row[8 * c4 + 2] | ((uint32_t)row[8 * c4 + 3] << 16),
+                             (uint32_t)row[8 * c4 + 4] | ((uint32_t)row[8 * c4 + 5] << 16), (uint32_t)row[8 * c4 + 6] | ((uint32_t)row[8 * c4 + 7] << 16));
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                       // A rows, gates and this run's token rows are visible
+#pragma unroll 1
+    for (int pt = 0; pt < kMmaRun / 16; ++pt) {
+      if (pt * 16 >= n) break;
+      const int r0 = pt * 16 + gq;
+      uint32_t af[2][2][4];
+#pragma unroll
+      for (int v = 0; v < 2; ++v)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const uint32_t* a0 = as + (v * kMmaRun + r0) * kMmaAS + s * 8 + tq;
+          af[v][s][0] = a0[0]; af[v][s][1] = a0[8 * kMmaAS]; af[v][s][2] = a0[4]; af[v][s][3] = a0[8 * kMmaAS + 4];
+        }
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        float d1[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(d1, af[0][0], bf[j][0][0][0], bf[j][0][0][1]);
+        mma_bf16_16816(d1, af[0][1], bf[j][0][1][0], bf[j][0][1][1]);
+        mma_bf16_16816(d2, af[1][0], bf[j][1][0][0], bf[j][1][0][1]);
+        mma_bf16_16816(d2, af[1][1], bf[j][1][1][0], bf[j][1][1][1]);
+        const int pos0 = (warp * 6 + j) * 8 + tq * 2;
+        const bool pad = ((pos0 + 1) & 15) == 15;
+        const float padv = pos0 < 96 ? 1.0f : 0.f;        // q pads carry the constant 1 (k-gen bias rider), v pads 0
+        const float2 g1 = *reinterpret_cast<const float2*>(gs + pos0), g2 = *reinterpret_cast<const float2*>(gs + kCp + pos0);
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int row = r0 + 8 * hh;
+          const float* xr = xs + row * kMmaXS + cA[j];
+          const float xa = xr[0], xb = xr[pad ? 0 : 1];
+          const float l1a = fmaxf(d1[2 * hh], 0.2f * d1[2 * hh]), l1b = fmaxf(d1[2 * hh + 1], 0.2f * d1[2 * hh + 1]);     // LeakyReLU(0.2) (:329)
+          const float l2a = fmaxf(d2[2 * hh], 0.2f * d2[2 * hh]), l2b = fmaxf(d2[2 * hh + 1], 0.2f * d2[2 * hh + 1]);
+          const float o0 = fmaf(g2.x, l2a, fmaf(g1.x, l1a, xa));                                                        // (:345-359)
+          const float o1 = pad ? padv : fmaf(g2.y, l2b, fmaf(g1.y, l1b, xb));
+          os[row * kMmaOS + (pos0 >> 1)] = pack_bf16x2(o0, o1);
+        }
+      }
+    }
+    __syncthreads();                                       // output tile complete, token rows consumed
+    if (xs0 + kMmaRun < g.Wp) stage_x(xs0 + kMmaRun);     // the next run's rows arrive while this tile is copied out
+    bf16* trow = trow0 + (long long)xs0 * kCp;
+    for (int q = tid; q < n * 24; q += 128) {
+      const int px = q / 24, part = q - px * 24;
+      *reinterpret_cast<uint4*>(trow + (long long)px * kCp + part * 8) = *reinterpret_cast<const uint4*>(os + px * kMmaOS + part * 4);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // UnionAttention statistics.  X = a (+ b).
 //   rows kernel : CTA per (b, y): channel mean/max per pixel + mean/max over W per channel.
 //   cols kernel : CTA per (b, x): mean/max over H per channel.
@@ -641,6 +814,14 @@ int launch_sca_mlp(const float* part_sum, const float* part_max, int nparts, Pad
 int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, const float* cmax, const float* s1, const float* s2, CasaW w, bf16* t,
                      cudaStream_t st) {
   if (casa) {
+    static const bool simt = getenv("HITSIR_CASA") != nullptr && strcmp(getenv("HITSIR_CASA"), "simt") == 0;   // A/B switch: the SIMT gate
+    if (w.bfrag != nullptr && !simt) {
+      static unsigned long long configured = 0;
+      if (ensure_dynamic_smem(qkv_casa_mma_kernel, kMmaSmem, &configured)) return 1;
+      qkv_casa_mma_kernel<<<g.B * g.Hp, 128, kMmaSmem, st>>>(x, g, cavg, cmax, s1, s2, w.bfrag, t);
+      HITSIR_CHECK(cudaGetLastError());
+      return 0;
+    }
     const int runs = (g.Wp + kQkvRun - 1) / kQkvRun;
     qkv_casa_kernel<<<g.B * g.Hp * runs, 96, 0, st>>>(x, g, cavg, cmax, s1, s2, w, t, runs);
     HITSIR_CHECK(cudaGetLastError());
@@ -648,6 +829,12 @@ int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, con
   }
   const long long total = (long long)g.B * g.Hp * g.Wp * (kCp / 8);
   qkv_build_kernel<<<grid_for(total, 192), 192, 0, st>>>(x, g, t);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int casa_bfrag_words() { return kCasaBfragWords; }
+int launch_pack_casa_bfrag(CasaW w, uint32_t* img, cudaStream_t st) {
+  casa_bfrag_kernel<<<(kCasaBfragWords + 255) / 256, 256, 0, st>>>(w, img);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

@@ -49,7 +49,10 @@ struct CasaW {
   const float* l1s_w; const float* l1s_b;   // [180][18], [180]
   const float* l2f_w; const float* l2f_b;
   const float* l2s_w; const float* l2s_b;
+  const uint32_t* bfrag;                 // linear1/linear2 as split-bf16 MMA B fragments (launch_pack_casa_bfrag); nullptr = SIMT gate
 };
+int casa_bfrag_words();
+int launch_pack_casa_bfrag(CasaW w, uint32_t* img, cudaStream_t st);
 struct PadGeom {
   int B, H, W, Hp, Wp;     // real and reflect-padded sizes
 };
