@@ -484,13 +484,20 @@ __global__ void __launch_bounds__(128) qkv_casa_mma_kernel(const float* __restri
   const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs);
   auto stage_x = [&](int xs0) {
     const int n = min(kMmaRun, g.Wp - xs0);
-    for (int q = tid; q < n * 45; q += 128) {
-      const int px = q / 45, ch = q - px * 45;
-      const float* src = xrow + (long long)reflect_src(xs0 + px, g.W) * kC + ch * 4;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(xs_addr + (uint32_t)(px * kMmaXS + ch * 4) * 4u), "l"(src) : "memory");
+    for (int px = warp; px < n; px += 4) {                 // a token row is 45 chunks of 16 bytes: lanes 0..31, then lanes 0..12
+      const float* src = xrow + (long long)reflect_src(xs0 + px, g.W) * kC + lane * 4;
+      const uint32_t dst = xs_addr + (uint32_t)(px * kMmaXS + lane * 4) * 4u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+      if (lane < 13) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(src + 128) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  float gv[3];                                             // 0.5 * channel gates of this image: fetched first, stored after the B fragments
+#pragma unroll
+  for (int e = 0; e < 3; ++e) {
+    const int i = tid + 128 * e, v = i / kCp, c = scc_chan(i - v * kCp);
+    gv[e] = c >= 0 ? 0.5f * (v == 0 ? s1 : s2)[(long long)b * kC + c] : 0.f;
+  }
   stage_x(0);
   // B fragments of this warp's six n-tiles and the per-column constants
   uint32_t bf[6][2][2][2];
@@ -506,10 +513,8 @@ __global__ void __launch_bounds__(128) qkv_casa_mma_kernel(const float* __restri
         for (int i = 0; i < 2; ++i) bf[j][v][s][i] = bfrag[((((nt * 2 + v) * 2 + s) * 2 + i) << 5) + lane];
     cA[j] = scc_chan(nt * 8 + tq * 2);                   // an even position is never a pad
   }
-  for (int i = tid; i < 2 * kCp; i += 128) {
-    const int v = i / kCp, pos = i - v * kCp, c = scc_chan(pos);
-    gs[i] = c >= 0 ? 0.5f * (v == 0 ? s1 : s2)[(long long)b * kC + c] : 0.f;
-  }
+#pragma unroll
+  for (int e = 0; e < 3; ++e) gs[tid + 128 * e] = gv[e];
   bf16* trow0 = t + ((long long)b * g.Hp + yp) * g.Wp * kCp;
   for (int xs0 = 0; xs0 < g.Wp; xs0 += kMmaRun) {
     const int n = min(kMmaRun, g.Wp - xs0);
@@ -581,10 +586,9 @@ __global__ void __launch_bounds__(128) qkv_casa_mma_kernel(const float* __restri
     __syncthreads();                                       // output tile complete, token rows consumed
     if (xs0 + kMmaRun < g.Wp) stage_x(xs0 + kMmaRun);     // the next run's rows arrive while this tile is copied out
     bf16* trow = trow0 + (long long)xs0 * kCp;
-    for (int q = tid; q < n * 24; q += 128) {
-      const int px = q / 24, part = q - px * 24;
-      *reinterpret_cast<uint4*>(trow + (long long)px * kCp + part * 8) = *reinterpret_cast<const uint4*>(os + px * kMmaOS + part * 4);
-    }
+    if (lane < 24)                                         // a bf16 token row is 24 chunks of 16 bytes
+      for (int px = warp; px < n; px += 4)
+        *reinterpret_cast<uint4*>(trow + (long long)px * kCp + lane * 8) = *reinterpret_cast<const uint4*>(os + px * kMmaOS + lane * 4);
   }
 }
 
