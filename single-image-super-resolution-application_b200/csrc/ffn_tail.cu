@@ -59,8 +59,13 @@ __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 compute warps
 
+template <bool kMma>
 __global__ void __launch_bounds__(640, 1)
 ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_dw, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_x, const Params p) {
@@ -360,6 +365,70 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
       for (int j = 0; j < 3; ++j) {
         const int k = half + 2 * j;
         const uint32_t u = (uint32_t)(it * 3 + j);
+        if constexpr (kMma) {
+          // ---- depthwise 5x5 on the tensor core: warp = 8 channels of the slice over the whole 8 x 16 tile.  One m16n8k16 MMA covers
+          // 16 pixels of an image row (M), 8 channels (N) and two horizontal taps (K = tap x channel, B = diag(w_tap) blocks), so an
+          // output row takes 5 x 3 MMAs.  Every fragment register is one 32-bit shared load of a channel pair of one pixel: the
+          // SWIZZLE_128B halo box puts the 8 pixels of a fragment column on 8 different bank groups.  Only 10 % of the MMA flops are
+          // useful and it still beats the FP32 pipe, which keeps the GELU and the LayerNorm epilogue to itself.
+          const uint8_t* hb = sp + kOffHalo + half * kHaloStage;
+          const uint32_t* tblu = reinterpret_cast<const uint32_t*>(hb + kHalo);          // [25][64] bf16 words by channel parity, [1][64] fp32 bias
+          const int cg = cw & 7, gq = lane >> 2, tq = lane & 3;
+          mbar_wait(halo_full(half), u & 1u);
+          uint32_t bfr[5][5];
+#pragma unroll
+          for (int ky = 0; ky < 5; ++ky)
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+              const uint32_t wv = tblu[(ky * 5 + dx) * 64 + cg * 8 + gq];
+              bfr[ky][dx] = (tq == (gq >> 1)) ? wv : 0u;                                   // B[k = channel][n = channel] is diagonal
+            }
+          const float2 bs = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tblu) + 25 * 64 + cg * 8 + 2 * tq);
+          uint32_t swz[8];                                                               // byte offset of this lane's word for pixel class c = (pixel - gq) & 7
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) swz[c8] = (uint32_t)gq * 128u + ((((uint32_t)cg) ^ ((uint32_t)(gq + c8) & 7u)) << 4) + (uint32_t)tq * 4u;
+          const uint32_t a_off = (uint32_t)gq * 128u + ((((uint32_t)cg) ^ (uint32_t)gq) << 4) + (uint32_t)tq * 4u;   // A-operand row gq (+ 8, + 16 yo)
+          const bool live = k * 64 + cg * 8 + 2 * tq < kHid;
+          float acc[8][4];
+#pragma unroll
+          for (int y = 0; y < 8; ++y) { acc[y][0] = bs.x; acc[y][1] = bs.y; acc[y][2] = bs.x; acc[y][3] = bs.y; }
+          uint32_t cen[8][2];
+#pragma unroll
+          for (int yi = 0; yi < kPH; ++yi) {
+            uint32_t F[5][2];
+#pragma unroll
+            for (int dx = 0; dx < 5; ++dx) {
+              const uint8_t* ptr = hb + (yi * kPW + dx) * 128 + swz[(yi * kPW + dx) & 7];
+              F[dx][0] = *reinterpret_cast<const uint32_t*>(ptr);
+              F[dx][1] = *reinterpret_cast<const uint32_t*>(ptr + 1024);
+            }
+            if (yi == kPH - 1) mbar_arrive_warp(halo_empty(half));                        // every input word of this warp is in registers
+#pragma unroll
+            for (int ky = 0; ky < 5; ++ky) {
+              const int yo = yi - ky;                                                      // compile-time after unrolling
+              if (yo >= 0 && yo < 8) {
+                mma_bf16_16816(acc[yo], F[0][0], F[0][1], F[1][0], F[1][1], bfr[ky][0], bfr[ky][1]);
+                mma_bf16_16816(acc[yo], F[2][0], F[2][1], F[3][0], F[3][1], bfr[ky][2], bfr[ky][3]);
+                mma_bf16_16816(acc[yo], F[4][0], F[4][1], 0u, 0u, bfr[ky][4], 0u);
+              }
+            }
+            if (yi >= 2 && yi < 10) { cen[yi - 2][0] = F[2][0]; cen[yi - 2][1] = F[2][1]; }
+            if (yi == 4) mbar_wait(a_empty(half), (u & 1u) ^ 1u);                          // the MMAs of the previous use of this A buffer are done
+            if (yi >= 4) {                                                                 // output row yo is complete: GELU + input -> fc2 A operand
+              const int yo = yi - 4;
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                const float2 cv = unpack_bf16x2_alu(cen[yo][hh]);
+                const float2 gl = gelu2(make_float2(acc[yo][2 * hh], acc[yo][2 * hh + 1]));
+                const float2 h2 = __fadd2_rn(cv, gl);
+                const uint32_t o = live ? pack_bf16x2(h2.x, h2.y) : 0u;
+                *reinterpret_cast<uint32_t*>(abuf + (yo * 16 + 8 * hh) * 128 + a_off) = o;
+              }
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive_warp(a_full(half));
+        } else {
         const int c = k * 64 + 2 * lane;
         const bool live = c < kHid;
         mbar_wait(halo_full(half), u & 1u);
@@ -409,6 +478,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         }
         fence_proxy_async_smem();
         mbar_arrive_warp(a_full(half));
+        }
         if (it > 0) {
           if (j == 0) epi_begin(it - 1, tpp);
           epi_group(it - 1, j);
@@ -432,11 +502,14 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
 
 }  // namespace
 
-// h1: bf16 [B,H,W,384]; fc2 packed weights tensor map (box {64, 192}); x: fp32 residual stream [B,H,W,180], updated in place
-int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
+// h1: bf16 [B,H,W,384]; fc2 packed weights tensor map (box {64, 192}); x: fp32 residual stream [B,H,W,180], updated in place.
+// dw_tbl_mma != nullptr selects the tensor-core depthwise conv (table of launch_pack_dw_mma), else the SIMT conv on the fp32 table dw_tbl.
+int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
                     const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st) {
-  static unsigned long long configured = 0;
-  if (ensure_dynamic_smem(ffn_tail_kernel, kSmemBytes, &configured)) return 1;
+  const bool mma = dw_tbl_mma != nullptr;
+  static unsigned long long configured[2] = {0, 0};
+  if (mma ? ensure_dynamic_smem(ffn_tail_kernel<true>, kSmemBytes, &configured[1]) : ensure_dynamic_smem(ffn_tail_kernel<false>, kSmemBytes, &configured[0]))
+    return 1;
   Params p;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 7) / 8;
@@ -447,11 +520,12 @@ int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const CUtensorMap& tm_w
   p.cavg = p.cmax = p.part_sum = p.part_max = nullptr; p.Hp = H; p.Wp = W;
   if (stats != nullptr) { p.cavg = stats->cavg; p.cmax = stats->cmax; p.part_sum = stats->part_sum; p.part_max = stats->part_max; p.Hp = stats->Hp; p.Wp = stats->Wp; }
   CUtensorMap tm_h1, tm_x, tm_dw;
-  if (make_tmap_2d_plain(&tm_dw, dw_tbl, 4, kHidp, 26, (uint64_t)kHidp * 4, 64, 26)) return 1;
-  if (make_tmap_nhwc_plain(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH)) return 1;
+  if (make_tmap_2d_plain(&tm_dw, mma ? (const void*)dw_tbl_mma : (const void*)dw_tbl, 4, kHidp, 26, (uint64_t)kHidp * 4, 64, 26)) return 1;
+  if (mma ? make_tmap_nhwc(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH) : make_tmap_nhwc_plain(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH)) return 1;
   if (make_tmap_nhwc_t(&tm_x, x, 4, B, H, W, kC, kC, 32, 16, 8)) return 1;
   const int grid = p.total < num_sms ? p.total : num_sms;
-  ffn_tail_kernel<<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_dw, tm_w2, tm_x, p);
+  if (mma) ffn_tail_kernel<true><<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_dw, tm_w2, tm_x, p);
+  else ffn_tail_kernel<false><<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_dw, tm_w2, tm_x, p);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

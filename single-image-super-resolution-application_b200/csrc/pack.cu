@@ -100,6 +100,16 @@ __global__ void pack_tapmajor_kernel(const float* __restrict__ w, float* __restr
   }
 }
 
+// depthwise taps as MMA B-fragment words (ffn_tail.cu): bf16(w) in the half selected by the channel parity; the bias row stays fp32
+__global__ void pack_dw_mma_kernel(const float* __restrict__ tbl, uint32_t* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 26 * kHidp) return;
+  const int tap = idx / kHidp, c = idx - tap * kHidp;
+  if (tap == 25) { out[idx] = __float_as_uint(tbl[idx]); return; }
+  const bf16 h = __float2bfloat16_rn(tbl[idx]);
+  out[idx] = (uint32_t)(*reinterpret_cast<const uint16_t*>(&h)) << (16 * (c & 1));
+}
+
 __device__ __forceinline__ void ln_relu(float* v, int n, const float* g, const float* b) {
   float m = 0.f;
   for (int i = 0; i < n; ++i) m += v[i];
@@ -177,6 +187,11 @@ int launch_pack_firstconv(const float* w, const float* b, bf16* wp, float* bp, i
 }
 int launch_pack_tapmajor(const float* w, float* out, int C, int taps, int Cpad, cudaStream_t st) {
   pack_tapmajor_kernel<<<grid_for((long long)taps * Cpad, 256), 256, 0, st>>>(w, out, C, taps, Cpad);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pack_dw_mma(const float* dw_tbl, uint32_t* out, cudaStream_t st) {
+  pack_dw_mma_kernel<<<grid_for(26 * kHidp, 256), 256, 0, st>>>(dw_tbl, out);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
