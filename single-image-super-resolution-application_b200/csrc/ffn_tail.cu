@@ -63,6 +63,12 @@ __device__ __forceinline__ void mma_bf16_16816(float* d, uint32_t a0, uint32_t a
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr) : "memory");
+}
+__device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 compute warps
 
 template <bool kMma>
@@ -368,8 +374,8 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         if constexpr (kMma) {
           // ---- depthwise 5x5 on the tensor core: warp = 8 channels of the slice over the whole 8 x 16 tile.  One m16n8k16 MMA covers
           // 16 pixels of an image row (M), 8 channels (N) and two horizontal taps (K = tap x channel, B = diag(w_tap) blocks), so an
-          // output row takes 5 x 3 MMAs.  Every fragment register is one 32-bit shared load of a channel pair of one pixel: the
-          // SWIZZLE_128B halo box puts the 8 pixels of a fragment column on 8 different bank groups.  Only 10 % of the MMA flops are
+          // output row takes 5 x 3 MMAs.  A fragments come from ldmatrix (a matrix row = 8 channels of one pixel = one 16-byte chunk): the
+          // SWIZZLE_128B halo box puts the 8 pixels of a matrix on 8 different bank groups, so every load is conflict-free.  Only 10 % of the MMA flops are
           // useful and it still beats the FP32 pipe, which keeps the GELU and the LayerNorm epilogue to itself.
           const uint8_t* hb = sp + kOffHalo + half * kHaloStage;
           const uint32_t* tblu = reinterpret_cast<const uint32_t*>(hb + kHalo);          // [25][64] bf16 words by channel parity, [1][64] fp32 bias
@@ -384,9 +390,12 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
               bfr[ky][dx] = (tq == (gq >> 1)) ? wv : 0u;                                   // B[k = channel][n = channel] is diagonal
             }
           const float2 bs = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tblu) + 25 * 64 + cg * 8 + 2 * tq);
-          uint32_t swz[8];                                                               // byte offset of this lane's word for pixel class c = (pixel - gq) & 7
+          // ldmatrix row of this lane: matrix m = lane >> 3 holds pixels (m & 1) * 8 .. + 7 of tap dx + (m >> 1); four byte offsets cover the
+          // swizzle classes (pixel & 7) that the even window origins 4 yi + 2 s can take
+          const uint32_t lj = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8 + (lane >> 4));
+          uint32_t swz[4];
 #pragma unroll
-          for (int c8 = 0; c8 < 8; ++c8) swz[c8] = (uint32_t)gq * 128u + ((((uint32_t)cg) ^ ((uint32_t)(gq + c8) & 7u)) << 4) + (uint32_t)tq * 4u;
+          for (int c4 = 0; c4 < 4; ++c4) swz[c4] = smem_u32(hb) + lj * 128u + ((((uint32_t)cg) ^ ((lj + 2u * (uint32_t)c4) & 7u)) << 4);
           const uint32_t a_off = (uint32_t)gq * 128u + ((((uint32_t)cg) ^ (uint32_t)gq) << 4) + (uint32_t)tq * 4u;   // A-operand row gq (+ 8, + 16 yo)
           const bool live = k * 64 + cg * 8 + 2 * tq < kHid;
           float acc[8][4];
@@ -397,21 +406,20 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
           for (int yi = 0; yi < kPH; ++yi) {
             uint32_t F[5][2];
 #pragma unroll
-            for (int dx = 0; dx < 5; ++dx) {
-              const uint8_t* ptr = hb + (yi * kPW + dx) * 128 + swz[(yi * kPW + dx) & 7];
-              F[dx][0] = *reinterpret_cast<const uint32_t*>(ptr);
-              F[dx][1] = *reinterpret_cast<const uint32_t*>(ptr + 1024);
-            }
+            for (int sx = 0; sx < 2; ++sx)
+              ldmatrix_x4(swz[((4 * yi + 2 * sx) & 7) >> 1] + (uint32_t)((yi * kPW + 2 * sx) * 128), F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1]);
+            ldmatrix_x2(swz[((4 * yi + 4) & 7) >> 1] + (uint32_t)((yi * kPW + 4) * 128), F[4][0], F[4][1]);
             if (yi == kPH - 1) mbar_arrive_warp(halo_empty(half));                        // every input word of this warp is in registers
 #pragma unroll
-            for (int ky = 0; ky < 5; ++ky) {
-              const int yo = yi - ky;                                                      // compile-time after unrolling
-              if (yo >= 0 && yo < 8) {
-                mma_bf16_16816(acc[yo], F[0][0], F[0][1], F[1][0], F[1][1], bfr[ky][0], bfr[ky][1]);
-                mma_bf16_16816(acc[yo], F[2][0], F[2][1], F[3][0], F[3][1], bfr[ky][2], bfr[ky][3]);
-                mma_bf16_16816(acc[yo], F[4][0], F[4][1], 0u, 0u, bfr[ky][4], 0u);
+            for (int sx = 0; sx < 3; ++sx)                                                 // consecutive MMAs go to different output rows
+#pragma unroll
+              for (int ky = 0; ky < 5; ++ky) {
+                const int yo = yi - ky;                                                    // compile-time after unrolling
+                if (yo >= 0 && yo < 8) {
+                  if (sx < 2) mma_bf16_16816(acc[yo], F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1], bfr[ky][2 * sx], bfr[ky][2 * sx + 1]);
+                  else mma_bf16_16816(acc[yo], F[4][0], F[4][1], 0u, 0u, bfr[ky][4], 0u);
+                }
               }
-            }
             if (yi >= 2 && yi < 10) { cen[yi - 2][0] = F[2][0]; cen[yi - 2][1] = F[2][1]; }
             if (yi == 4) mbar_wait(a_empty(half), (u & 1u) ^ 1u);                          // the MMAs of the previous use of this A buffer are done
             if (yi >= 4) {                                                                 // output row yo is complete: GELU + input -> fc2 A operand
