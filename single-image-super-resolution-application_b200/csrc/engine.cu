@@ -91,7 +91,6 @@ struct HitsirHandle {
   int device = 0;
   int num_sms = 148;
   bool simt = false;
-  bool dw_simt = false;           // HITSIR_DWCONV=simt: FP32-pipe depthwise conv inside ffn_tail (A/B switch; default = mma.sync path)
   bool no_epilogue_stats = false; // HITSIR_STATS=kernel: always compute the casa statistics with the stand-alone sca_stats pass
   bool ffn_unfused = false;       // HITSIR_FFN=unfused: separate dwconv5 and fc2 kernels for every block
   bool scc_gram_only = false;     // HITSIR_SCC=gram: use the Gram-matrix kernel (scc_umma.cu) for every window size
@@ -707,7 +706,7 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
       fs = FfnStats{ws.cavg, ws.cmax, ws.part_sum, ws.part_max, round_up(f.H, wn), round_up(f.W, wn)};
       fsp = &fs;
     }
-    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_w, h->dw_simt ? nullptr : bw.dw_mma, bw.fc2.tm, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, fsp, h->num_sms, f.st));
+    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_mma, bw.fc2.tm, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, fsp, h->num_sms, f.st));
     if (fsp != nullptr) f.stats_nparts = ffn_tiles_per_image(f.H, f.W);
     if (need_shadow) LAUNCH("cast_shadow", 1, launch_cast_rows_bf16(xout, ws.xb0, f.N, f.st));
   } else {
@@ -905,8 +904,6 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
   h->simt = env && strcmp(env, "simt") == 0;
   const char* env5 = getenv("HITSIR_STATS");
   h->no_epilogue_stats = env5 && strcmp(env5, "kernel") == 0;
-  const char* env6 = getenv("HITSIR_DWCONV");
-  h->dw_simt = env6 && strcmp(env6, "simt") == 0;
   const char* env4 = getenv("HITSIR_FFN");
   h->ffn_unfused = env4 && strcmp(env4, "unfused") == 0;
   const char* env3 = getenv("HITSIR_SCC");

@@ -1,16 +1,20 @@
 // Second half of ConvFFN fused into one persistent kernel (/root/reference/models/hit_sir_pro.py:42-46 with :15-17, and the
 // post-norm residual of HierarchicalTransformerBlock.forward :704):
-//     h2 = h1 + GELU(dwconv5x5(h1) + b_dw)            (SIMT, FP32-FMA-bound: 16 conv warps)
+//     h2 = h1 + GELU(dwconv5x5(h1) + b_dw)            (warp-level bf16 MMAs with block-diagonal taps + packed-fp32 GELU)
 //     x  = x + LayerNorm(h2 W2^T + b2)                 (tcgen05, accumulator in TMEM, LayerNorm in the epilogue)
 // The 360-channel hidden map h2 never goes to HBM: per 8 x 16 pixel tile the conv warps produce it 64 channels at a time straight
 // into the SWIZZLE_128B K-major A-operand buffers of the fc2 contraction, while the TMA producer streams the (8+4) x (16+4) x 64
 // halo boxes of h1 (zero padding = out-of-bounds fill) and the matching 64-column slices of W2.  Standalone, the depthwise conv
-// wrote and fc2 re-read 1536 B per token and fc2 sat at the HBM roofline; fused, fc2's traffic hides under the conv's FMA time.
+// wrote and fc2 re-read 1536 B per token and fc2 sat at the HBM roofline; fused, fc2's traffic hides under the conv.
 //
-// Warp roles (640 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = residual/output box DMA,
-// 4..19 = compute.  Compute warps 0-7 / 8-15 ("halves") convolve the even / odd 64-channel slices (one 4x4 pixel block per warp,
-// lane = channel pair, 25 taps in registers); afterwards all 16 warps run the LayerNorm epilogue (warp = TMEM lane quarter x
-// 16-column slice).  Halo stage, A buffer and W2 stage h belong to half h, so every ring is a plain two-slot ping-pong.
+// The depthwise conv is a tensor-core contraction: an FP32-pipe version (25 FFMA per output, 3 distinct 64-bit operands per FFMA2 =
+// 3 issue cycles, tools/ubench/ffma2_rate.cu) bound the kernel at 2.2-2.4 ms; m16n8k16 MMAs with B = diag(tap weights) waste 90 % of
+// their flops and still run the 25 taps of 16 pixels x 8 channels in 15 instructions.
+//
+// Warp roles (640 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator / statistics, 3 = residual/output box DMA,
+// 4..19 = compute.  All 16 compute warps work on the same 64-channel slice (warp = 8 channels x 4 output rows of the tile); halo stage,
+// A buffer and W2 stage ping-pong with the slice parity, so the next slice's halo is in flight while this one is convolved.  After every
+// second slice the same warps run one 64-column group of the PREVIOUS tile's LayerNorm epilogue (warp = TMEM lane quarter x 16-column slice).
 #include "gemm.cuh"
 #include "kernels.cuh"
 
@@ -71,7 +75,6 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 compute warps
 
-template <bool kMma>
 __global__ void __launch_bounds__(640, 1)
 ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_dw, const __grid_constant__ CUtensorMap tm_w,
                 const __grid_constant__ CUtensorMap tm_x, const Params p) {
@@ -103,8 +106,8 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_h1); tma_prefetch_desc(&tm_dw); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_x); }
   if (warp == 1 && lane == 0) {
     for (int h = 0; h < 2; ++h) {
-      mbar_init(halo_full(h), 1); mbar_init(halo_empty(h), 8);
-      mbar_init(a_full(h), 8); mbar_init(a_empty(h), 1);
+      mbar_init(halo_full(h), 1); mbar_init(halo_empty(h), 16);
+      mbar_init(a_full(h), 16); mbar_init(a_empty(h), 1);
       mbar_init(w_full(h), 1); mbar_init(w_empty(h), 1);
       mbar_init(d_full(h), 1); mbar_init(d_empty(h), 16);
     }
@@ -250,15 +253,12 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
   } else if (warp >= 4) {
     // ===================== compute warps =====================
     const int cw = warp - 4;
-    const int half = cw >> 3;                              // conv role: slices k = half, half + 2, half + 4
-    const int by = ((cw & 7) >> 2) * 4, bx = ((cw & 7) & 3) * 4;     // conv role: 4 x 4 block of the 8 x 16 tile
+    const int cg = cw & 7, rh = cw >> 3;                   // conv role: 8 channels of the slice, output rows 4 rh .. 4 rh + 3 of the tile
+    const int gq = lane >> 2, tq = lane & 3;               // MMA fragment coordinates
     const int q = warp & 3, hs = cw >> 2;                  // epilogue role: TMEM lane quarter, 16-column slice of every 64-column group
     const int r = q * 32 + lane;
     const uint32_t rsw = (uint32_t)(r & 7);
     uint8_t* row_ptr = sp + kOffBox + r * 128;
-    const uint32_t* halo = reinterpret_cast<const uint32_t*>(sp + kOffHalo + half * kHaloStage) + lane;      // + pixel * 32 words
-    const float2* wtab = reinterpret_cast<const float2*>(sp + kOffHalo + half * kHaloStage + kHalo) + lane;   // + tap * 32: this lane's channel pair
-    uint8_t* abuf = sp + kOffA + half * kABuf;
     // per-pixel channel mean / max of a finished tile (the casa gate's 3x3 convs read them, :345-347): the four slice partials of a row
     // are exchanged through s_part2 and flushed by the hs == 0 thread after the NEXT barrier of the compute warps (no extra barrier)
     auto flush_pixel_stats = [&](int tprev, int itprev) {
@@ -364,132 +364,80 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         if (want_stats) s_part2[(e & 1) * 512 + hs * 128 + r] = make_float2(e_ls, e_lm);   // flushed after the next tile's LayerNorm barrier
       }
     };
+    // ldmatrix row of this lane: matrix m = lane >> 3 holds pixels (m & 1) * 8 .. + 7 of tap dx + (m >> 1); four byte offsets cover the
+    // swizzle classes (pixel & 7) that the even window origins 4 yi + 2 s can take (the halo row pitch is 20 = 4 mod 8 pixels)
+    const uint32_t lj = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8 + (lane >> 4));
+    uint32_t swz[4];
+#pragma unroll
+    for (int c4 = 0; c4 < 4; ++c4)
+      swz[c4] = sb + kOffHalo + (uint32_t)(rh * 4 * kPW) * 128u + lj * 128u + ((((uint32_t)cg) ^ ((lj + 2u * (uint32_t)c4) & 7u)) << 4);
+    // fc2 A-operand word of this lane: tile pixel row (4 rh + yo) * 16 + gq (+ 8), 16-byte chunk cg, channel pair tq
+    const uint32_t a_off = (uint32_t)(rh * 4 * 16 + gq) * 128u + ((((uint32_t)cg) ^ (uint32_t)gq) << 4) + (uint32_t)tq * 4u;
     int it = 0, tprev = -1, tpp = -1;
     for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
-      // ---------- depthwise 5x5 + GELU + input on this half's three slices -> A operand; after slice j, group j of the previous tile's epilogue
+      // ---------- depthwise 5x5 + GELU + input, slice by slice -> A operand; after every second slice one group of the previous tile's epilogue.
+      // One m16n8k16 MMA covers 16 pixels of an image row (M), 8 channels (N) and two horizontal taps (K = tap x channel, B = diag(w_tap)
+      // blocks), so an output row takes 5 x 3 MMAs.  A fragments come from ldmatrix (a matrix row = 8 channels of one pixel = one 16-byte
+      // chunk): the SWIZZLE_128B halo box puts the 8 pixels of a matrix on 8 different bank groups, so every load is conflict-free.
 #pragma unroll 1
-      for (int j = 0; j < 3; ++j) {
-        const int k = half + 2 * j;
-        const uint32_t u = (uint32_t)(it * 3 + j);
-        if constexpr (kMma) {
-          // ---- depthwise 5x5 on the tensor core: warp = 8 channels of the slice over the whole 8 x 16 tile.  One m16n8k16 MMA covers
-          // 16 pixels of an image row (M), 8 channels (N) and two horizontal taps (K = tap x channel, B = diag(w_tap) blocks), so an
-          // output row takes 5 x 3 MMAs.  A fragments come from ldmatrix (a matrix row = 8 channels of one pixel = one 16-byte chunk): the
-          // SWIZZLE_128B halo box puts the 8 pixels of a matrix on 8 different bank groups, so every load is conflict-free.  Only 10 % of the MMA flops are
-          // useful and it still beats the FP32 pipe, which keeps the GELU and the LayerNorm epilogue to itself.
-          const uint8_t* hb = sp + kOffHalo + half * kHaloStage;
-          const uint32_t* tblu = reinterpret_cast<const uint32_t*>(hb + kHalo);          // [25][64] bf16 words by channel parity, [1][64] fp32 bias
-          const int cg = cw & 7, gq = lane >> 2, tq = lane & 3;
-          mbar_wait(halo_full(half), u & 1u);
-          uint32_t bfr[5][5];
+      for (int k = 0; k < 6; ++k) {
+        const int h = k & 1;
+        const uint32_t u = (uint32_t)(it * 3 + (k >> 1));
+        const uint32_t* tblu = reinterpret_cast<const uint32_t*>(sp + kOffHalo + h * kHaloStage + kHalo);   // [25][64] bf16 words by channel parity, [1][64] fp32 bias
+        uint8_t* abuf = sp + kOffA + h * kABuf;
+        const uint32_t hoff = (uint32_t)(h * kHaloStage);
+        mbar_wait(halo_full(h), u & 1u);
+        uint32_t bfr[5][5];
 #pragma unroll
-          for (int ky = 0; ky < 5; ++ky)
+        for (int ky = 0; ky < 5; ++ky)
 #pragma unroll
-            for (int dx = 0; dx < 5; ++dx) {
-              const uint32_t wv = tblu[(ky * 5 + dx) * 64 + cg * 8 + gq];
-              bfr[ky][dx] = (tq == (gq >> 1)) ? wv : 0u;                                   // B[k = channel][n = channel] is diagonal
-            }
-          const float2 bs = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tblu) + 25 * 64 + cg * 8 + 2 * tq);
-          // ldmatrix row of this lane: matrix m = lane >> 3 holds pixels (m & 1) * 8 .. + 7 of tap dx + (m >> 1); four byte offsets cover the
-          // swizzle classes (pixel & 7) that the even window origins 4 yi + 2 s can take
-          const uint32_t lj = (uint32_t)((lane & 7) + ((lane >> 3) & 1) * 8 + (lane >> 4));
-          uint32_t swz[4];
+          for (int dx = 0; dx < 5; ++dx) {
+            const uint32_t wv = tblu[(ky * 5 + dx) * 64 + cg * 8 + gq];
+            bfr[ky][dx] = (tq == (gq >> 1)) ? wv : 0u;                                     // B[k = channel][n = channel] is diagonal
+          }
+        const float2 bs = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tblu) + 25 * 64 + cg * 8 + 2 * tq);
+        const bool live = k * 64 + cg * 8 + 2 * tq < kHid;
+        float acc[4][4];
 #pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) swz[c4] = smem_u32(hb) + lj * 128u + ((((uint32_t)cg) ^ ((lj + 2u * (uint32_t)c4) & 7u)) << 4);
-          const uint32_t a_off = (uint32_t)gq * 128u + ((((uint32_t)cg) ^ (uint32_t)gq) << 4) + (uint32_t)tq * 4u;   // A-operand row gq (+ 8, + 16 yo)
-          const bool live = k * 64 + cg * 8 + 2 * tq < kHid;
-          float acc[8][4];
+        for (int y = 0; y < 4; ++y) { acc[y][0] = bs.x; acc[y][1] = bs.y; acc[y][2] = bs.x; acc[y][3] = bs.y; }
+        uint32_t cen[4][2];
 #pragma unroll
-          for (int y = 0; y < 8; ++y) { acc[y][0] = bs.x; acc[y][1] = bs.y; acc[y][2] = bs.x; acc[y][3] = bs.y; }
-          uint32_t cen[8][2];
+        for (int yr = 0; yr < 8; ++yr) {                                                   // input row 4 rh + yr of the halo box
+          uint32_t F[5][2];
 #pragma unroll
-          for (int yi = 0; yi < kPH; ++yi) {
-            uint32_t F[5][2];
+          for (int sx = 0; sx < 2; ++sx)
+            ldmatrix_x4(swz[((4 * yr + 2 * sx) & 7) >> 1] + hoff + (uint32_t)((yr * kPW + 2 * sx) * 128), F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1]);
+          ldmatrix_x2(swz[((4 * yr + 4) & 7) >> 1] + hoff + (uint32_t)((yr * kPW + 4) * 128), F[4][0], F[4][1]);
+          if (yr == 7) mbar_arrive_warp(halo_empty(h));                                    // every input word of this warp is in registers
 #pragma unroll
-            for (int sx = 0; sx < 2; ++sx)
-              ldmatrix_x4(swz[((4 * yi + 2 * sx) & 7) >> 1] + (uint32_t)((yi * kPW + 2 * sx) * 128), F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1]);
-            ldmatrix_x2(swz[((4 * yi + 4) & 7) >> 1] + (uint32_t)((yi * kPW + 4) * 128), F[4][0], F[4][1]);
-            if (yi == kPH - 1) mbar_arrive_warp(halo_empty(half));                        // every input word of this warp is in registers
+          for (int sx = 0; sx < 3; ++sx)                                                   // consecutive MMAs go to different output rows
 #pragma unroll
-            for (int sx = 0; sx < 3; ++sx)                                                 // consecutive MMAs go to different output rows
-#pragma unroll
-              for (int ky = 0; ky < 5; ++ky) {
-                const int yo = yi - ky;                                                    // compile-time after unrolling
-                if (yo >= 0 && yo < 8) {
-                  if (sx < 2) mma_bf16_16816(acc[yo], F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1], bfr[ky][2 * sx], bfr[ky][2 * sx + 1]);
-                  else mma_bf16_16816(acc[yo], F[4][0], F[4][1], 0u, 0u, bfr[ky][4], 0u);
-                }
-              }
-            if (yi >= 2 && yi < 10) { cen[yi - 2][0] = F[2][0]; cen[yi - 2][1] = F[2][1]; }
-            if (yi == 4) mbar_wait(a_empty(half), (u & 1u) ^ 1u);                          // the MMAs of the previous use of this A buffer are done
-            if (yi >= 4) {                                                                 // output row yo is complete: GELU + input -> fc2 A operand
-              const int yo = yi - 4;
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                const float2 cv = unpack_bf16x2_alu(cen[yo][hh]);
-                const float2 gl = gelu2(make_float2(acc[yo][2 * hh], acc[yo][2 * hh + 1]));
-                const float2 h2 = __fadd2_rn(cv, gl);
-                const uint32_t o = live ? pack_bf16x2(h2.x, h2.y) : 0u;
-                *reinterpret_cast<uint32_t*>(abuf + (yo * 16 + 8 * hh) * 128 + a_off) = o;
+            for (int ky = 0; ky < 5; ++ky) {
+              const int yo = yr - ky;                                                      // compile-time after unrolling
+              if (yo >= 0 && yo < 4) {
+                if (sx < 2) mma_bf16_16816(acc[yo], F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1], bfr[ky][2 * sx], bfr[ky][2 * sx + 1]);
+                else mma_bf16_16816(acc[yo], F[4][0], F[4][1], 0u, 0u, bfr[ky][4], 0u);
               }
             }
-          }
-          fence_proxy_async_smem();
-          mbar_arrive_warp(a_full(half));
-        } else {
-        const int c = k * 64 + 2 * lane;
-        const bool live = c < kHid;
-        mbar_wait(halo_full(half), u & 1u);
-        const float2 bs = wtab[25 * 32];
-        float2 acc[4][4];
+          if (yr >= 2 && yr < 6) { cen[yr - 2][0] = F[2][0]; cen[yr - 2][1] = F[2][1]; }
+          if (yr == 4) mbar_wait(a_empty(h), (u & 1u) ^ 1u);                               // the fc2 MMAs of the previous use of this A buffer are done
+          if (yr >= 4) {                                                                   // output row yo is complete: GELU + input -> fc2 A operand
+            const int yo = yr - 4;
 #pragma unroll
-        for (int oy = 0; oy < 4; ++oy)
-#pragma unroll
-          for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = bs;
-        uint32_t center[4][4];
-        const uint32_t* tp0 = halo + (by * kPW + bx) * 32;
-#pragma unroll
-        for (int iy = 0; iy < 8; ++iy) {
-          float2 in[8];
-#pragma unroll
-          for (int ix = 0; ix < 8; ++ix) {
-            const uint32_t v = tp0[(iy * kPW + ix) * 32];
-            in[ix] = unpack_bf16x2_alu(v);
-            if (iy >= 2 && iy < 6 && ix >= 2 && ix < 6) center[iy - 2][ix - 2] = v;
-          }
-#pragma unroll
-          for (int ky = 0; ky < 5; ++ky) {
-            const int oy = iy - ky;                        // compile-time after unrolling
-            if (oy >= 0 && oy < 4) {                        // runs of four FFMA2 share the tap: the multiplier comes from the operand-reuse cache
-#pragma unroll
-              for (int kx = 0; kx < 5; ++kx) {
-                const float2 wt = wtab[(ky * 5 + kx) * 32];
-#pragma unroll
-                for (int ox = 0; ox < 4; ++ox) acc[oy][ox] = __ffma2_rn(in[ox + kx], wt, acc[oy][ox]);
-              }
+            for (int hh = 0; hh < 2; ++hh) {
+              const float2 cv = unpack_bf16x2_alu(cen[yo][hh]);
+              const float2 gl = gelu2(make_float2(acc[yo][2 * hh], acc[yo][2 * hh + 1]));
+              const float2 h2 = __fadd2_rn(cv, gl);
+              const uint32_t o = live ? pack_bf16x2(h2.x, h2.y) : 0u;
+              *reinterpret_cast<uint32_t*>(abuf + (yo * 16 + 8 * hh) * 128 + a_off) = o;
             }
-          }
-        }
-        mbar_arrive_warp(halo_empty(half));                // every input word of this warp is in registers
-        mbar_wait(a_empty(half), (u & 1u) ^ 1u);           // the MMAs of the previous use of this A buffer are done
-#pragma unroll
-        for (int oy = 0; oy < 4; ++oy) {
-#pragma unroll
-          for (int ox = 0; ox < 4; ++ox) {
-            const float2 cv = unpack_bf16x2_alu(center[oy][ox]);
-            const float2 g = gelu2(acc[oy][ox]);
-            const float2 h2 = __fadd2_rn(cv, g);
-            const uint32_t o = live ? pack_bf16x2(h2.x, h2.y) : 0u;
-            const int row = (by + oy) * 16 + bx + ox;      // A row = pixel of the 8 x 16 tile
-            *reinterpret_cast<uint32_t*>(abuf + row * 128 + ((((uint32_t)lane >> 2) ^ (uint32_t)(row & 7)) << 4) + (lane & 3) * 4) = o;
           }
         }
         fence_proxy_async_smem();
-        mbar_arrive_warp(a_full(half));
-        }
-        if (it > 0) {
-          if (j == 0) epi_begin(it - 1, tpp);
-          epi_group(it - 1, j);
+        mbar_arrive_warp(a_full(h));
+        if (it > 0 && h == 1) {
+          if (k == 1) epi_begin(it - 1, tpp);
+          epi_group(it - 1, k >> 1);
         }
       }
       tpp = tprev; tprev = t;
@@ -510,14 +458,12 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
 
 }  // namespace
 
-// h1: bf16 [B,H,W,384]; fc2 packed weights tensor map (box {64, 192}); x: fp32 residual stream [B,H,W,180], updated in place.
-// dw_tbl_mma != nullptr selects the tensor-core depthwise conv (table of launch_pack_dw_mma), else the SIMT conv on the fp32 table dw_tbl.
-int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
+// h1: bf16 [B,H,W,384]; dw_tbl_mma: depthwise taps as B-fragment words + fp32 bias row (launch_pack_dw_mma); fc2 packed weights tensor
+// map (box {64, 192}); x: fp32 residual stream [B,H,W,180], updated in place
+int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
                     const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st) {
-  const bool mma = dw_tbl_mma != nullptr;
-  static unsigned long long configured[2] = {0, 0};
-  if (mma ? ensure_dynamic_smem(ffn_tail_kernel<true>, kSmemBytes, &configured[1]) : ensure_dynamic_smem(ffn_tail_kernel<false>, kSmemBytes, &configured[0]))
-    return 1;
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(ffn_tail_kernel, kSmemBytes, &configured)) return 1;
   Params p;
   p.B = B; p.H = H; p.W = W;
   p.tiles_x = (W + 15) / 16; p.tiles_y = (H + 7) / 8;
@@ -528,12 +474,11 @@ int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const uint32_t* dw_tbl_
   p.cavg = p.cmax = p.part_sum = p.part_max = nullptr; p.Hp = H; p.Wp = W;
   if (stats != nullptr) { p.cavg = stats->cavg; p.cmax = stats->cmax; p.part_sum = stats->part_sum; p.part_max = stats->part_max; p.Hp = stats->Hp; p.Wp = stats->Wp; }
   CUtensorMap tm_h1, tm_x, tm_dw;
-  if (make_tmap_2d_plain(&tm_dw, mma ? (const void*)dw_tbl_mma : (const void*)dw_tbl, 4, kHidp, 26, (uint64_t)kHidp * 4, 64, 26)) return 1;
-  if (mma ? make_tmap_nhwc(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH) : make_tmap_nhwc_plain(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH)) return 1;
+  if (make_tmap_2d_plain(&tm_dw, dw_tbl_mma, 4, kHidp, 26, (uint64_t)kHidp * 4, 64, 26)) return 1;
+  if (make_tmap_nhwc(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH)) return 1;               // SWIZZLE_128B halo boxes, zero fill outside the image
   if (make_tmap_nhwc_t(&tm_x, x, 4, B, H, W, kC, kC, 32, 16, 8)) return 1;
   const int grid = p.total < num_sms ? p.total : num_sms;
-  if (mma) ffn_tail_kernel<true><<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_dw, tm_w2, tm_x, p);
-  else ffn_tail_kernel<false><<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_dw, tm_w2, tm_x, p);
+  ffn_tail_kernel<<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_dw, tm_w2, tm_x, p);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

@@ -25,10 +25,10 @@ int launch_dwconv5_gelu_add(const bf16* h1, const float* w_tap_major, const floa
 // cavg/cmax [B*H*W], part_sum/part_max [B * tiles][180] with tiles = ceil(H/8) * ceil(W/16) 8x16-pixel tiles per image
 struct FfnStats { float* cavg; float* cmax; float* part_sum; float* part_max; int Hp, Wp; };
 inline int ffn_tiles_per_image(int H, int W) { return ((H + 7) / 8) * ((W + 15) / 16); }
-// dw_tbl: fp32 [26][384] = 25 tap rows + bias row (SIMT depthwise conv); dw_tbl_mma (launch_pack_dw_mma, may be nullptr): the same table as
-// B-fragment words of the tensor-core depthwise conv: row t < 25 = bf16(w[t][c]) in the low (c even) / high (c odd) half, row 25 = fp32 bias bits
+// dw_tbl_mma (launch_pack_dw_mma from the fp32 [26][384] tap-major table): the depthwise taps as B-fragment words of the tensor-core
+// conv: row t < 25 = bf16(w[t][c]) in the low (c even) / high (c odd) half, row 25 = fp32 bias bits
 int launch_pack_dw_mma(const float* dw_tbl, uint32_t* out, cudaStream_t st);
-int launch_ffn_tail(const bf16* h1, const float* dw_tbl, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
+int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
                     const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st);
 // nearest x2 upsample of an NHWC bf16 map with C channels
 int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st);
