@@ -9,7 +9,7 @@
 //
 // The depthwise conv is a tensor-core contraction: an FP32-pipe version (25 FFMA per output, 3 distinct 64-bit operands per FFMA2 =
 // 3 issue cycles, tools/ubench/ffma2_rate.cu) bound the kernel at 2.2-2.4 ms; m16n8k16 MMAs with B = diag(tap weights) waste 90 % of
-// their flops and still run the 25 taps of 16 pixels x 8 channels in 15 instructions.
+// their flops and still run the 25 taps of 16 pixels x 8 channels in 13 instructions.
 //
 // Warp roles (640 threads): 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator / statistics, 3 = residual/output box DMA,
 // 4..19 = compute.  All 16 compute warps work on the same 64-channel slice (warp = 8 channels x 4 output rows of the tile); halo stage,
@@ -73,7 +73,8 @@ __device__ __forceinline__ void ldmatrix_x4(uint32_t addr, uint32_t& r0, uint32_
 __device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_t& r1) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr) : "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }   // the 16 compute warps
+// the four compute warps that share a TMEM lane quarter (= the same 32 pixel rows) exchange their LayerNorm / statistics partials
+__device__ __forceinline__ void epi_bar_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 
 __global__ void __launch_bounds__(640, 1)
 ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_dw, const __grid_constant__ CUtensorMap tm_w,
@@ -316,7 +317,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
       }
       float2* part = s_part + (e & 1) * 512;
       part[hs * 128 + r] = make_float2(mean, m2);
-      epi_bar_sync();
+      epi_bar_sync(q);
       if (want_stats && tflush >= 0) flush_pixel_stats(tflush, e - 1);
 #pragma unroll
       for (int o = 1; o < 4; ++o) {
@@ -377,7 +378,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
     for (int t = blockIdx.x; t < p.total; t += gridDim.x, ++it) {
       // ---------- depthwise 5x5 + GELU + input, slice by slice -> A operand; after every second slice one group of the previous tile's epilogue.
       // One m16n8k16 MMA covers 16 pixels of an image row (M), 8 channels (N) and two horizontal taps (K = tap x channel, B = diag(w_tap)
-      // blocks), so an output row takes 5 x 3 MMAs.  A fragments come from ldmatrix (a matrix row = 8 channels of one pixel = one 16-byte
+      // blocks), so an output row takes 13 MMAs (10 for taps dx = 0..3, 3 for the dx = 4 column paired vertically).  A fragments come from ldmatrix (a matrix row = 8 channels of one pixel = one 16-byte
       // chunk): the SWIZZLE_128B halo box puts the 8 pixels of a matrix on 8 different bank groups, so every load is conflict-free.
 #pragma unroll 1
       for (int k = 0; k < 6; ++k) {
@@ -401,6 +402,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
 #pragma unroll
         for (int y = 0; y < 4; ++y) { acc[y][0] = bs.x; acc[y][1] = bs.y; acc[y][2] = bs.x; acc[y][3] = bs.y; }
         uint32_t cen[4][2];
+        uint32_t P4[2] = {0u, 0u};                                                         // dx = 4 fragments of the previous input row
 #pragma unroll
         for (int yr = 0; yr < 8; ++yr) {                                                   // input row 4 rh + yr of the halo box
           uint32_t F[5][2];
@@ -410,15 +412,17 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
           ldmatrix_x2(swz[((4 * yr + 4) & 7) >> 1] + hoff + (uint32_t)((yr * kPW + 4) * 128), F[4][0], F[4][1]);
           if (yr == 7) mbar_arrive_warp(halo_empty(h));                                    // every input word of this warp is in registers
 #pragma unroll
-          for (int sx = 0; sx < 3; ++sx)                                                   // consecutive MMAs go to different output rows
+          for (int sx = 0; sx < 2; ++sx)                                                   // taps dx = 0..3 in pairs; consecutive MMAs go to different output rows
 #pragma unroll
             for (int ky = 0; ky < 5; ++ky) {
               const int yo = yr - ky;                                                      // compile-time after unrolling
-              if (yo >= 0 && yo < 4) {
-                if (sx < 2) mma_bf16_16816(acc[yo], F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1], bfr[ky][2 * sx], bfr[ky][2 * sx + 1]);
-                else mma_bf16_16816(acc[yo], F[4][0], F[4][1], 0u, 0u, bfr[ky][4], 0u);
-              }
+              if (yo >= 0 && yo < 4) mma_bf16_16816(acc[yo], F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1], bfr[ky][2 * sx], bfr[ky][2 * sx + 1]);
             }
+          // the dx = 4 column pairs vertically: taps (0,4)+(1,4) and (2,4)+(3,4) take this row and the previous one, (4,4) stays single
+          if (yr - 1 >= 0 && yr - 1 < 4) mma_bf16_16816(acc[yr - 1], P4[0], P4[1], F[4][0], F[4][1], bfr[0][4], bfr[1][4]);
+          if (yr - 3 >= 0 && yr - 3 < 4) mma_bf16_16816(acc[yr - 3], P4[0], P4[1], F[4][0], F[4][1], bfr[2][4], bfr[3][4]);
+          if (yr - 4 >= 0 && yr - 4 < 4) mma_bf16_16816(acc[yr - 4], F[4][0], F[4][1], 0u, 0u, bfr[4][4], 0u);
+          P4[0] = F[4][0]; P4[1] = F[4][1];
           if (yr >= 2 && yr < 6) { cen[yr - 2][0] = F[2][0]; cen[yr - 2][1] = F[2][1]; }
           if (yr == 4) mbar_wait(a_empty(h), (u & 1u) ^ 1u);                               // the fc2 MMAs of the previous use of this A buffer are done
           if (yr >= 4) {                                                                   // output row yo is complete: GELU + input -> fc2 A operand
@@ -446,7 +450,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
       epi_begin(it - 1, tpp);
       for (int g = 0; g < 3; ++g) epi_group(it - 1, g);
     }
-    if (want_stats && tprev >= 0) { epi_bar_sync(); flush_pixel_stats(tprev, it - 1); }
+    if (want_stats && tprev >= 0) { epi_bar_sync(q); flush_pixel_stats(tprev, it - 1); }
   }
   tc_fence_before();
   __syncthreads();
