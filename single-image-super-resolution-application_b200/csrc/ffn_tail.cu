@@ -424,19 +424,19 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
           if (yr - 4 >= 0 && yr - 4 < 4) mma_bf16_16816(acc[yr - 4], F[4][0], F[4][1], 0u, 0u, bfr[4][4], 0u);
           P4[0] = F[4][0]; P4[1] = F[4][1];
           if (yr >= 2 && yr < 6) { cen[yr - 2][0] = F[2][0]; cen[yr - 2][1] = F[2][1]; }
-          if (yr == 4) mbar_wait(a_empty(h), (u & 1u) ^ 1u);                               // the fc2 MMAs of the previous use of this A buffer are done
-          if (yr >= 4) {                                                                   // output row yo is complete: GELU + input -> fc2 A operand
-            const int yo = yr - 4;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              const float2 cv = unpack_bf16x2_alu(cen[yo][hh]);
-              const float2 gl = gelu2(make_float2(acc[yo][2 * hh], acc[yo][2 * hh + 1]));
-              const float2 h2 = __fadd2_rn(cv, gl);
-              const uint32_t o = live ? pack_bf16x2(h2.x, h2.y) : 0u;
-              *reinterpret_cast<uint32_t*>(abuf + (yo * 16 + 8 * hh) * 128 + a_off) = o;
-            }
-          }
         }
+        // GELU + input -> fc2 A operand for all 8 channel pairs of this lane at once: eight independent ex2 / rcp chains hide the MUFU latency
+        mbar_wait(a_empty(h), (u & 1u) ^ 1u);                                              // the fc2 MMAs of the previous use of this A buffer are done
+#pragma unroll
+        for (int yo = 0; yo < 4; ++yo)
+#pragma unroll
+          for (int hh = 0; hh < 2; ++hh) {
+            const float2 cv = unpack_bf16x2_alu(cen[yo][hh]);
+            const float2 gl = gelu2(make_float2(acc[yo][2 * hh], acc[yo][2 * hh + 1]));
+            const float2 h2 = __fadd2_rn(cv, gl);
+            const uint32_t o = live ? pack_bf16x2(h2.x, h2.y) : 0u;
+            *reinterpret_cast<uint32_t*>(abuf + (yo * 16 + 8 * hh) * 128 + a_off) = o;
+          }
         fence_proxy_async_smem();
         mbar_arrive_warp(a_full(h));
         if (it > 0 && h == 1) {
