@@ -227,9 +227,17 @@ def run_ours(args):
     else:
         roof = {"bound": "tensor", "kernel": cat, "achieved": round(tflops, 2) if tflops else None, "peak": pk["bf16_sustained"],
                 "unit": "TFLOP/s", "frac": round(f_t, 4) if tflops else None, "algorithmic_flops_per_launch": fl}
-    if cat in ("ffn_tail", "dwconv5"):
-        # these kernels are bound by the FP32 FMA pipe of the depthwise 5x5 (25 FMA per hidden element, GELU polynomial not counted):
-        # 148 SMs x 128 FMA/clk at the sampled SM clock
+    if cat == "ffn_tail":
+        # the depthwise 5x5 of this kernel runs as warp-level m16n8k16 MMAs with block-diagonal taps (13 per 16 px x 8 ch output row):
+        # 8x16-pixel tiles x 6 slices x 16 warps x 52.  Peak = one MMA per 7.34 cycles per SM sub-partition, measured with
+        # tools/ubench/mma_rate.cu on this pool's B200 (4 sub-partitions x 148 SMs at the sampled SM clock).
+        tiles = B * -(-H // 8) * -(-W // 16)
+        mma = tiles * 6 * 16 * 52 / t_launch
+        mma_peak = 148 * 4 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 7.34
+        roof["warp_mma_m16n8k16"] = {"achieved_gmma_s": round(mma / 1e9, 2), "peak_gmma_s": round(mma_peak / 1e9, 2), "frac": round(mma / mma_peak, 4),
+                                     "useful_flop_fraction": round(25 / (13 * 16), 3)}
+    elif cat == "dwconv5":
+        # stand-alone SIMT depthwise path (HITSIR_FFN=unfused): 25 FP32 FMA per hidden element, 148 SMs x 128 FMA/clk at the sampled SM clock
         fma = N_tok * 360 * 25 / t_launch
         fma_peak = 148 * 128 * (clocks.get("sm_mhz") or 1965.0) * 1e6
         roof["simt_fp32_fma"] = {"achieved_tfma_s": round(fma / 1e12, 2), "peak_tfma_s": round(fma_peak / 1e12, 2), "frac": round(fma / fma_peak, 4)}
