@@ -114,6 +114,16 @@ HITSIR_API int hitsir_forward_host(HitsirHandle* h, const float* host_x, float* 
 HITSIR_API int hitsir_forward_u8(HitsirHandle* h, const uint8_t* x_hwc, uint8_t* y_hwc, int B, int H, int W,
                       float* dev_x, float* dev_y, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The evaluation metric around the path on the device (experiments/experiment.py:436-463, called per batch from :743-755): both fp32
+ * NCHW batches [B,3,H,W] in [0,1] are converted to the Y channel of YCbCr exactly as utils/utils.py:170-186 does
+ * (16/255 + (65.738 R + 129.057 G + 25.064 B) / 256, fp32), `sr` clipped to [0,1] first when clip_sr != 0 (experiment.py:746-748),
+ * and mse_out[b] (device, double) receives the mean squared Y difference of image b: PSNR_b = 10 log10(1 / mse_out[b])
+ * (skimage.metrics.peak_signal_noise_ratio, data_range=1).  `scratch`: device buffer of hitsir_psnr_y_scratch_doubles(B,H,W) doubles.
+ * Fixed-order reduction (bitwise reproducible); asynchronous on `stream`; needs no handle. */
+HITSIR_API int64_t hitsir_psnr_y_scratch_doubles(int B, int H, int W);
+HITSIR_API int hitsir_psnr_y(const float* sr, const float* hr, int B, int H, int W, int clip_sr, double* scratch, double* mse_out,
+                  void* stream);
+
 /* Test hook standing in for PyTorch forward hooks on reference sub-modules: the next
  * hitsir_forward copies the named intermediate activation (fp32, NHWC, real channels only) into
  * `dst` (device) and, when `stop` != 0, returns right after producing it.  Names: "shallow",

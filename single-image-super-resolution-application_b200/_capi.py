@@ -54,6 +54,8 @@ SYMBOLS = {
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "hitsir_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "hitsir_psnr_y_scratch_doubles": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "hitsir_psnr_y": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hitsir_set_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int]),
     "hitsir_last_launch_count": (C.c_int64, [C.c_void_p]),
     "hitsir_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),

@@ -1004,6 +1004,18 @@ HITSIR_API int hitsir_forward_u8(HitsirHandle* h, const uint8_t* x_hwc, uint8_t*
   return 0;
 }
 
+HITSIR_API int64_t hitsir_psnr_y_scratch_doubles(int B, int H, int W) {
+  if (B <= 0 || H <= 0 || W <= 0) return 0;
+  return (int64_t)B * psnr_y_chunks(H, W);
+}
+
+HITSIR_API int hitsir_psnr_y(const float* sr, const float* hr, int B, int H, int W, int clip_sr, double* scratch, double* mse_out, void* stream) {
+  if (!sr || !hr || !scratch || !mse_out) { set_error("hitsir_psnr_y: null argument"); return HITSIR_ERR_INVALID; }
+  if (B <= 0 || H <= 0 || W <= 0) { set_error("hitsir_psnr_y: bad shape %d x %d x %d", B, H, W); return HITSIR_ERR_INVALID; }
+  if (launch_psnr_y(sr, hr, B, H, W, clip_sr, scratch, mse_out, (cudaStream_t)stream)) return HITSIR_ERR_CUDA;
+  return 0;
+}
+
 HITSIR_API int hitsir_set_tap(HitsirHandle* h, const char* name, float* dst, int64_t dst_floats, int stop) {
   if (!h) { set_error("null handle"); return HITSIR_ERR_INVALID; }
   if (!name) { h->tap = Tap(); return 0; }
