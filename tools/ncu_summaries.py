@@ -15,7 +15,7 @@ import re
 import subprocess
 import sys
 
-PACKING = ("pack_", "pos_table", "pooled_bias", "scc_images", "casa_bfrag", "fill_", "tap_kernel")
+PACKING = ("pack_", "pos_table", "pooled_bias", "_image_kernel", "casa_bfrag", "fill_", "tap_kernel", "at::", "distribution_elementwise")
 COLS = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread", "gpu__time_duration.sum", "dram__bytes_read.sum",
         "dram__bytes_write.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
