@@ -340,24 +340,36 @@ __global__ void __launch_bounds__(256) sca_stats_kernel(const float* __restrict_
   }
 }
 
-// one CTA per image: finish the global pools, then Linear C->18->C twice (no activation, :350-355)
-__global__ void __launch_bounds__(192) sca_mlp_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_max, int nparts, PadGeom g,
+// one CTA per image: finish the global pools, then Linear C->18->C twice (no activation, :350-355).  768 threads: the partials are summed
+// by four groups of 192 channel threads (fixed order within a group, groups merged in order), the 36 length-180 dot products of the first
+// linears take one warp each (fixed shuffle tree): deterministic, and the serial chains that made this launch 54 us long are gone.
+__global__ void __launch_bounds__(768) sca_mlp_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_max, int nparts, PadGeom g,
                                                       CasaW w, float* __restrict__ s1, float* __restrict__ s2) {
-  __shared__ float avg[kC], mx[kC], h1[18], h2[18];
-  const int b = blockIdx.x, c = threadIdx.x;
+  __shared__ float ps[4][kCp], pm[4][kCp], avg[kC], mx[kC], h1[18], h2[18];
+  const int b = blockIdx.x, grp = threadIdx.x / 192, c = threadIdx.x - grp * 192;
   if (c < kC) {
     float s = 0.f, m = -INFINITY;
-    for (int p = 0; p < nparts; ++p) { s += part_sum[((long long)b * nparts + p) * kC + c]; m = fmaxf(m, part_max[((long long)b * nparts + p) * kC + c]); }
-    avg[c] = s / (float)(g.Hp * g.Wp); mx[c] = m;
+    for (int p = grp; p < nparts; p += 4) { s += part_sum[((long long)b * nparts + p) * kC + c]; m = fmaxf(m, part_max[((long long)b * nparts + p) * kC + c]); }
+    ps[grp][c] = s; pm[grp][c] = m;
   }
   __syncthreads();
-  if (c < 18) {
-    float a = w.l1f_b[c], bb = w.l2f_b[c];
-    for (int k = 0; k < kC; ++k) { a += w.l1f_w[c * kC + k] * avg[k]; bb += w.l2f_w[c * kC + k] * mx[k]; }
-    h1[c] = a; h2[c] = bb;
+  if (grp == 0 && c < kC) {
+    avg[c] = (((ps[0][c] + ps[1][c]) + ps[2][c]) + ps[3][c]) / (float)(g.Hp * g.Wp);
+    mx[c] = fmaxf(fmaxf(pm[0][c], pm[1][c]), fmaxf(pm[2][c], pm[3][c]));
   }
   __syncthreads();
-  if (c < kC) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int o = warp; o < 36; o += 24) {                    // outputs 0..17: linear1_first on the average pool, 18..35: linear2_first on the max pool
+    const int j = o % 18;
+    const float* wr = (o < 18 ? w.l1f_w : w.l2f_w) + j * kC;
+    const float* v = o < 18 ? avg : mx;
+    float a = 0.f;
+    for (int k = lane; k < kC; k += 32) a = fmaf(wr[k], v[k], a);
+    a = warp_sum(a);
+    if (lane == 0) { if (o < 18) h1[j] = a + w.l1f_b[j]; else h2[j] = a + w.l2f_b[j]; }
+  }
+  __syncthreads();
+  if (grp == 0 && c < kC) {
     float a = w.l1s_b[c], bb = w.l2s_b[c];
 #pragma unroll
     for (int k = 0; k < 18; ++k) { a += w.l1s_w[c * 18 + k] * h1[k]; bb += w.l2s_w[c * 18 + k] * h2[k]; }
@@ -866,7 +878,7 @@ int launch_sca_stats(const float* x, PadGeom g, float* cavg, float* cmax, float*
   return 0;
 }
 int launch_sca_mlp(const float* part_sum, const float* part_max, int nparts, PadGeom g, CasaW w, float* s1, float* s2, cudaStream_t st) {
-  sca_mlp_kernel<<<g.B, 192, 0, st>>>(part_sum, part_max, nparts, g, w, s1, s2);
+  sca_mlp_kernel<<<g.B, 768, 0, st>>>(part_sum, part_max, nparts, g, w, s1, s2);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
