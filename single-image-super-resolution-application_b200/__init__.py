@@ -12,5 +12,6 @@ from . import _capi  # noqa: F401
 from .sharding import ShardedSR, tile_plan, stitch_tiles  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401
 from .metrics import mse_y, psnr_y  # noqa: F401
+from .graphed import GraphedForward  # noqa: F401
 
-__all__ = ["HiT_SIR", "PRO_KWARGS", "ShardedSR", "tile_plan", "stitch_tiles", "HostPipeline", "mse_y", "psnr_y"]
+__all__ = ["HiT_SIR", "PRO_KWARGS", "ShardedSR", "tile_plan", "stitch_tiles", "HostPipeline", "mse_y", "psnr_y", "GraphedForward"]

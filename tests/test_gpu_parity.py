@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 import torch
 
+import hitsir_b200
+
 from oracle.weights import synthetic_image
 from tests.helpers import GOLDEN_CASES, TAP_REL_L2, assert_close, build_pair, load_golden, psnr, rel_l2
 
@@ -199,3 +201,33 @@ def test_forward_uint8_matches_float_pipeline_bit_exactly():
     assert torch.equal(y_u8, expect)
     ref_u8 = (ref.clip(0, 1) * 255.0).to(torch.uint8).permute(0, 2, 3, 1)
     assert (y_u8.int() - ref_u8.int()).abs().max().item() <= 1
+
+
+def test_graphed_forward_replays_bit_exactly_and_faster():
+    """CUDA-graph replay of the 263-launch forward (launch-bound 1x3x64x64 case): same bits as the eager call."""
+    import time
+    model = hitsir_b200.HiT_SIR(True, True, True, **hitsir_b200.PRO_KWARGS).eval().to(DEV)
+    x1 = synthetic_image(1, 64, 64, seed=11).to(DEV)
+    x2 = synthetic_image(1, 64, 64, seed=12).to(DEV)
+    with torch.no_grad():
+        e1 = model(x1).clone()
+        e2 = model(x2).clone()
+    g = hitsir_b200.GraphedForward(model, x1)
+    assert torch.equal(g(x1), e1)
+    assert torch.equal(g(x2), e2)
+    assert torch.equal(g(x1), e1)
+
+    def timed(fn, n=20):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+    with torch.no_grad():
+        t_eager = timed(lambda: model(x1))
+    t_graph = timed(lambda: g(x1))
+    print(f"1x3x64x64 forward: eager {t_eager:.2f} ms, graph replay {t_graph:.2f} ms")
+    assert t_graph < 1.2 * t_eager
+    with pytest.raises(RuntimeError):
+        g(synthetic_image(1, 48, 64, seed=1).to(DEV))
