@@ -396,7 +396,7 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
       bw.dw_b = bw.dw_w + 25 * kHidp;
       if (launch_pack_tapmajor(P(h, p + ".mlp.dwconv.depthwise_conv.0.weight"), bw.dw_w, kHid, 25, kHidp, st)) return 1;
       if (launch_pack_tapmajor(P(h, p + ".mlp.dwconv.depthwise_conv.0.bias"), bw.dw_b, kHid, 1, kHidp, st)) return 1;
-      if (dev_alloc(h, &bw.dw_mma, 26 * kHidp)) return 1;
+      if (dev_alloc(h, &bw.dw_mma, 28 * kHidp)) return 1;
       if (launch_pack_dw_mma(bw.dw_w, bw.dw_mma, st)) return 1;
     }
     if (make_gemm_w(h, &h->layer_conv[i], "layers." + std::to_string(i) + ".conv", C, C, 9, st)) return 1;

@@ -24,7 +24,8 @@ namespace {
 
 constexpr int kPH = 12, kPW = 20;                         // halo patch of an 8 x 16 tile
 constexpr int kHalo = kPH * kPW * 128;                    // 30720 B, dense 128-byte pixel rows (no swizzle)
-constexpr int kDwTbl = 26 * 64 * 4;                       // 25 taps + bias of the slice's 64 channels, fp32
+constexpr int kDwRow = 28;                                // words per channel of the tap table (kernels.cuh launch_pack_dw_mma)
+constexpr int kDwTbl = 64 * kDwRow * 4;                   // the slice's 64 channel rows
 constexpr int kHaloStage = 37 * 1024;                     // halo box + tap table, padded to keep the next region 1024-byte aligned
 static_assert(kHalo + kDwTbl <= kHaloStage, "halo stage");
 constexpr int kABuf = 128 * 128;                          // A operand: 128 pixels x 64 ch bf16, SWIZZLE_128B
@@ -39,7 +40,8 @@ constexpr int kOffPar = kOffBox + kNBox * kBoxBytes;      // bias | gamma | beta
 constexpr int kOffPart = kOffPar + 3 * 192 * 4;           // LayerNorm partials [2][4][128] float2
 constexpr int kOffPart2 = kOffPart + 2 * 4 * 128 * 8;      // per-pixel channel (sum, max) partials [4][128] float2
 constexpr int kOffMult = kOffPart2 + 2 * 4 * 128 * 8;     // (double-buffered by tile parity); reflect multiplicity of the tile's 128 pixels (0 = outside the image)
-constexpr int kOffBars = kOffMult + 128 * 4;
+constexpr int kOffZero = kOffMult + 128 * 4;                // 128 zero bytes: the tap row of the lanes whose B-fragment words are off-diagonal
+constexpr int kOffBars = kOffZero + 128;
 constexpr int kNumBars = 40;
 constexpr int kSmemBytes = kOffBars + kNumBars * 8 + 16 + 1024;
 static_assert(kSmemBytes <= 232448, "smem budget");
@@ -116,6 +118,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }   // warp 2 later doubles as the statistics warp
+  if (threadIdx.x < 32) reinterpret_cast<uint32_t*>(sp + kOffZero)[threadIdx.x] = 0u;
   for (int i = threadIdx.x; i < 192; i += blockDim.x) {
     s_bias[i] = p.bias[i];
     s_gamma[i] = i < kC ? p.gamma[i] : 0.f;
@@ -143,7 +146,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
           mbar_wait(halo_empty(h), (u & 1u) ^ 1u);
           mbar_expect_tx(halo_full(h), kHalo + kDwTbl);
           tma_load_4d(sb + kOffHalo + h * kHaloStage, &tm_h1, halo_full(h), k * 64, x0 - 2, y0 - 2, b);
-          tma_load_2d(sb + kOffHalo + h * kHaloStage + kHalo, &tm_dw, halo_full(h), k * 64, 0);
+          tma_load_2d(sb + kOffHalo + h * kHaloStage + kHalo, &tm_dw, halo_full(h), 0, k * 64);
           mbar_wait(w_empty(h), (u & 1u) ^ 1u);
           mbar_expect_tx(w_full(h), kWStage);
           tma_load_2d(sb + kOffWs + h * kWStage, &tm_w, w_full(h), k * 64, 0);
@@ -384,19 +387,18 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
       for (int k = 0; k < 6; ++k) {
         const int h = k & 1;
         const uint32_t u = (uint32_t)(it * 3 + (k >> 1));
-        const uint32_t* tblu = reinterpret_cast<const uint32_t*>(sp + kOffHalo + h * kHaloStage + kHalo);   // [25][64] bf16 words by channel parity, [1][64] fp32 bias
+        // tap rows [64 channels][28 words]: 5 x (taps dx = 0..3 of row ky), then (0,4) (1,4) (2,4) (3,4), then (4,4) 0 bias 0 -- the order in which
+        // the MMAs pair them.  B[k = channel][n = channel] is diagonal: only the lane with tq == gq / 2 holds non-zero words (in the half chosen
+        // by the channel parity at pack time); every other lane reads the zero row, so the whole set-up is seven 16-byte loads.
+        const uint32_t* tblu = reinterpret_cast<const uint32_t*>(sp + kOffHalo + h * kHaloStage + kHalo);
         uint8_t* abuf = sp + kOffA + h * kABuf;
         const uint32_t hoff = (uint32_t)(h * kHaloStage);
         mbar_wait(halo_full(h), u & 1u);
-        uint32_t bfr[5][5];
+        const uint4* brow = (tq == (gq >> 1)) ? reinterpret_cast<const uint4*>(tblu + (cg * 8 + gq) * kDwRow) : reinterpret_cast<const uint4*>(sp + kOffZero);
+        uint4 bq[7];
 #pragma unroll
-        for (int ky = 0; ky < 5; ++ky)
-#pragma unroll
-          for (int dx = 0; dx < 5; ++dx) {
-            const uint32_t wv = tblu[(ky * 5 + dx) * 64 + cg * 8 + gq];
-            bfr[ky][dx] = (tq == (gq >> 1)) ? wv : 0u;                                     // B[k = channel][n = channel] is diagonal
-          }
-        const float2 bs = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tblu) + 25 * 64 + cg * 8 + 2 * tq);
+        for (int i = 0; i < 7; ++i) bq[i] = brow[i];
+        const float2 bs = make_float2(__uint_as_float(tblu[(cg * 8 + 2 * tq) * kDwRow + 26]), __uint_as_float(tblu[(cg * 8 + 2 * tq + 1) * kDwRow + 26]));
         const bool live = k * 64 + cg * 8 + 2 * tq < kHid;
         float acc[4][4];
 #pragma unroll
@@ -416,12 +418,12 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
 #pragma unroll
             for (int ky = 0; ky < 5; ++ky) {
               const int yo = yr - ky;                                                      // compile-time after unrolling
-              if (yo >= 0 && yo < 4) mma_bf16_16816(acc[yo], F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1], bfr[ky][2 * sx], bfr[ky][2 * sx + 1]);
+              if (yo >= 0 && yo < 4) mma_bf16_16816(acc[yo], F[2 * sx][0], F[2 * sx][1], F[2 * sx + 1][0], F[2 * sx + 1][1], sx ? bq[ky].z : bq[ky].x, sx ? bq[ky].w : bq[ky].y);
             }
           // the dx = 4 column pairs vertically: taps (0,4)+(1,4) and (2,4)+(3,4) take this row and the previous one, (4,4) stays single
-          if (yr - 1 >= 0 && yr - 1 < 4) mma_bf16_16816(acc[yr - 1], P4[0], P4[1], F[4][0], F[4][1], bfr[0][4], bfr[1][4]);
-          if (yr - 3 >= 0 && yr - 3 < 4) mma_bf16_16816(acc[yr - 3], P4[0], P4[1], F[4][0], F[4][1], bfr[2][4], bfr[3][4]);
-          if (yr - 4 >= 0 && yr - 4 < 4) mma_bf16_16816(acc[yr - 4], F[4][0], F[4][1], 0u, 0u, bfr[4][4], 0u);
+          if (yr - 1 >= 0 && yr - 1 < 4) mma_bf16_16816(acc[yr - 1], P4[0], P4[1], F[4][0], F[4][1], bq[5].x, bq[5].y);
+          if (yr - 3 >= 0 && yr - 3 < 4) mma_bf16_16816(acc[yr - 3], P4[0], P4[1], F[4][0], F[4][1], bq[5].z, bq[5].w);
+          if (yr - 4 >= 0 && yr - 4 < 4) mma_bf16_16816(acc[yr - 4], F[4][0], F[4][1], 0u, 0u, bq[6].x, bq[6].y);
           P4[0] = F[4][0]; P4[1] = F[4][1];
           if (yr >= 2 && yr < 6) { cen[yr - 2][0] = F[2][0]; cen[yr - 2][1] = F[2][1]; }
         }
@@ -478,7 +480,7 @@ int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMa
   p.cavg = p.cmax = p.part_sum = p.part_max = nullptr; p.Hp = H; p.Wp = W;
   if (stats != nullptr) { p.cavg = stats->cavg; p.cmax = stats->cmax; p.part_sum = stats->part_sum; p.part_max = stats->part_max; p.Hp = stats->Hp; p.Wp = stats->Wp; }
   CUtensorMap tm_h1, tm_x, tm_dw;
-  if (make_tmap_2d_plain(&tm_dw, dw_tbl_mma, 4, kHidp, 26, (uint64_t)kHidp * 4, 64, 26)) return 1;
+  if (make_tmap_2d_plain(&tm_dw, dw_tbl_mma, 4, kDwRow, kHidp, (uint64_t)kDwRow * 4, kDwRow, 64)) return 1;
   if (make_tmap_nhwc(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH)) return 1;               // SWIZZLE_128B halo boxes, zero fill outside the image
   if (make_tmap_nhwc_t(&tm_x, x, 4, B, H, W, kC, kC, 32, 16, 8)) return 1;
   const int grid = p.total < num_sms ? p.total : num_sms;

@@ -26,7 +26,7 @@ int launch_dwconv5_gelu_add(const bf16* h1, const float* w_tap_major, const floa
 struct FfnStats { float* cavg; float* cmax; float* part_sum; float* part_max; int Hp, Wp; };
 inline int ffn_tiles_per_image(int H, int W) { return ((H + 7) / 8) * ((W + 15) / 16); }
 // dw_tbl_mma (launch_pack_dw_mma from the fp32 [26][384] tap-major table): the depthwise taps as B-fragment words of the tensor-core
-// conv: row t < 25 = bf16(w[t][c]) in the low (c even) / high (c odd) half, row 25 = fp32 bias bits
+// conv, [384 channels][28 words]: bf16(w) in the low (c even) / high (c odd) half in MMA pairing order, word 26 = fp32 bias bits (pack.cu)
 int launch_pack_dw_mma(const float* dw_tbl, uint32_t* out, cudaStream_t st);
 int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
                     const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st);

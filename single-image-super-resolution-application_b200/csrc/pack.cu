@@ -100,14 +100,25 @@ __global__ void pack_tapmajor_kernel(const float* __restrict__ w, float* __restr
   }
 }
 
-// depthwise taps as MMA B-fragment words (ffn_tail.cu): bf16(w) in the half selected by the channel parity; the bias row stays fp32
+// depthwise taps as MMA B-fragment words (ffn_tail.cu): one row of 28 words per channel, bf16(w) in the half selected by the channel parity,
+// in the order in which the 13 MMAs of an output row pair the taps: words 4 ky + dx (dx = 0..3), 20 + ky for the taps (ky, 4) with ky < 4,
+// 24 = tap (4,4), 26 = the bias as fp32 bits, 25 and 27 = 0.  tbl = fp32 tap-major table [26][384] (row 25 = bias).
 __global__ void pack_dw_mma_kernel(const float* __restrict__ tbl, uint32_t* __restrict__ out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 26 * kHidp) return;
-  const int tap = idx / kHidp, c = idx - tap * kHidp;
-  if (tap == 25) { out[idx] = __float_as_uint(tbl[idx]); return; }
-  const bf16 h = __float2bfloat16_rn(tbl[idx]);
-  out[idx] = (uint32_t)(*reinterpret_cast<const uint16_t*>(&h)) << (16 * (c & 1));
+  if (idx >= kHidp * 28) return;
+  const int c = idx / 28, wd = idx - c * 28;
+  int tap = -1;
+  if (wd < 20) tap = (wd >> 2) * 5 + (wd & 3);
+  else if (wd < 24) tap = (wd - 20) * 5 + 4;
+  else if (wd == 24) tap = 24;
+  uint32_t v = 0u;
+  if (tap >= 0) {
+    const bf16 h = __float2bfloat16_rn(tbl[tap * kHidp + c]);
+    v = (uint32_t)(*reinterpret_cast<const uint16_t*>(&h)) << (16 * (c & 1));
+  } else if (wd == 26) {
+    v = __float_as_uint(tbl[25 * kHidp + c]);
+  }
+  out[idx] = v;
 }
 
 __device__ __forceinline__ void ln_relu(float* v, int n, const float* g, const float* b) {
@@ -191,7 +202,7 @@ int launch_pack_tapmajor(const float* w, float* out, int C, int taps, int Cpad, 
   return 0;
 }
 int launch_pack_dw_mma(const float* dw_tbl, uint32_t* out, cudaStream_t st) {
-  pack_dw_mma_kernel<<<grid_for(26 * kHidp, 256), 256, 0, st>>>(dw_tbl, out);
+  pack_dw_mma_kernel<<<grid_for(28 * kHidp, 256), 256, 0, st>>>(dw_tbl, out);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
