@@ -18,7 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libhitsir_b200.so")
-SOURCES = ["engine.cu", "umma_gemm.cu", "umma_gemm_tma.cu", "conv3_c64.cu", "ffn_tail.cu", "simt_ref.cu", "scc_umma.cu", "scc_dense.cu", "glue.cu", "pack.cu"]
+SOURCES = ["engine.cu", "umma_gemm.cu", "umma_gemm_tma.cu", "conv3_c64.cu", "ffn_tail.cu", "proj_fc1.cu", "simt_ref.cu", "scc_umma.cu", "scc_dense.cu", "glue.cu", "pack.cu"]
 HEADERS = ["common.cuh", "gemm.cuh", "kernels.cuh", os.path.join("..", "..", "include", "hitsir_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -91,6 +91,7 @@ struct HitsirHandle {
   int device = 0;
   int num_sms = 148;
   bool simt = false;
+  bool projfc1_fused = false;     // HITSIR_PROJFC1=fused: proj + fc1 chained in one kernel (proj_fc1.cu; slower than the two GEMM launches so far)
   bool no_epilogue_stats = false; // HITSIR_STATS=kernel: always compute the casa statistics with the stand-alone sca_stats pass
   bool ffn_unfused = false;       // HITSIR_FFN=unfused: separate dwconv5 and fc2 kernels for every block
   bool scc_gram_only = false;     // HITSIR_SCC=gram: use the Gram-matrix kernel (scc_umma.cu) for every window size
@@ -686,6 +687,11 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   TAP((tn + ".sccdbg").c_str(), ws.scc_dbg, 0, kSccDbgFloats, 1, kSccDbgFloats);
   TAPP((tn + ".scc").c_str(), ws.outsc, 1, kCp, f.N, kC);
   GemmParams p;
+  if (!h->simt && !h->direct_epilogue && h->projfc1_fused && bw.proj.BN == 192 && bw.proj.K == 192 && bw.fc1.K == 192 && bw.fc1.Npad == 384) {
+    // proj + norm1 + residual and fc1 + GELU in one kernel (:597, :700-703, :39-41)
+    LAUNCH("proj_fc1", 1, launch_proj_fc1(ws.outsc, bw.proj.tm, bw.proj.b, bw.g1, bw.b1, xin, xout, bw.fc1.w, bw.fc1.b, ws.H1, f.N, h->num_sms, f.st));
+    TAP((tn + ".attn").c_str(), xout, 0, kC, f.N, kC);
+  } else {
   // proj + norm1 + residual (:597, :700-703)
   base_params(p, bw.proj);
   p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g1; p.beta = bw.b1; p.res = xin; p.ldr = kC;
@@ -696,6 +702,7 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   base_params(p, bw.fc1);
   p.epi = EPI_STORE; p.act = ACT_GELU; p.n_real = kHid; p.out_bf16 = ws.H1; p.ldb = kHidp;
   RUN(linear(f, "gemm_fc1_gelu", bw.fc1, ws.xb0, f.N, p));
+  }
   const bool need_shadow = (j == c.depths[i] - 1);      // the RHTB conv after the last block reads a bf16 shadow of the stream (:934)
   if (!h->simt && !h->direct_epilogue && !h->ffn_unfused) {
     // dwconv5 + GELU + input, fc2, norm2 and the residual add in one kernel: the hidden map h2 never reaches HBM
@@ -904,6 +911,8 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
   h->simt = env && strcmp(env, "simt") == 0;
   const char* env5 = getenv("HITSIR_STATS");
   h->no_epilogue_stats = env5 && strcmp(env5, "kernel") == 0;
+  const char* env7 = getenv("HITSIR_PROJFC1");
+  h->projfc1_fused = env7 && strcmp(env7, "fused") == 0;
   const char* env4 = getenv("HITSIR_FFN");
   h->ffn_unfused = env4 && strcmp(env4, "unfused") == 0;
   const char* env3 = getenv("HITSIR_SCC");

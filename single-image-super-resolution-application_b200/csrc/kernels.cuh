@@ -30,6 +30,10 @@ inline int ffn_tiles_per_image(int H, int W) { return ((H + 7) / 8) * ((W + 15) 
 int launch_pack_dw_mma(const float* dw_tbl, uint32_t* out, cudaStream_t st);
 int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
                     const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st);
+// proj_fc1.cu: proj + norm1 + residual chained with fc1 + GELU (the bf16 copy of the stream stays in shared memory); tm_wp = packed proj
+// weights (box {64, 192}), w1 = packed fc1 weights bf16 [384][192], res / xout fp32 [N][180], h1 bf16 [N][384]
+int launch_proj_fc1(const bf16* outsc, const CUtensorMap& tm_wp, const float* bp, const float* gamma, const float* beta, const float* res,
+                    float* xout, const bf16* w1, const float* b1, bf16* h1, long long N, int num_sms, cudaStream_t st);
 // nearest x2 upsample of an NHWC bf16 map with C channels
 int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st);
 int launch_fill_f32(float* p, float v, long long n, cudaStream_t st);

@@ -231,3 +231,19 @@ def test_graphed_forward_replays_bit_exactly_and_faster():
     assert t_graph < 1.2 * t_eager
     with pytest.raises(RuntimeError):
         g(synthetic_image(1, 48, 64, seed=1).to(DEV))
+
+
+def test_fused_proj_fc1_path_matches_default(monkeypatch):
+    """HITSIR_PROJFC1=fused (proj + norm1 + residual chained with fc1 + GELU in one kernel, csrc/proj_fc1.cu) is an opt-in A/B path:
+    same result as the two-launch default up to the bf16 rounding of the shadow copy (identical arithmetic otherwise)."""
+    x = synthetic_image(2, 40, 56, seed=9).to(DEV)
+    model, oracle = build_pair((1, 1, 1), "nearest+conv", 4, "stress", 17)
+    with torch.no_grad():
+        ref = oracle(x.cpu())
+        y0 = model.to(DEV)(x).cpu()
+    monkeypatch.setenv("HITSIR_PROJFC1", "fused")
+    model2, _ = build_pair((1, 1, 1), "nearest+conv", 4, "stress", 17)      # the switch is read when the handle is created
+    with torch.no_grad():
+        y1 = model2.to(DEV)(x).cpu()
+    assert_close(y1, ref, "stress")
+    assert_close(y1, y0, "stress")
