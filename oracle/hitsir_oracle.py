@@ -68,7 +68,7 @@ def dynamic_pos_bias_table(sd: Dict[str, Tensor], prefix: str, win: Tuple[int, i
     grid = torch.stack(torch.meshgrid(oh, ow, indexing="ij"))       # (2, 2wh-1, 2ww-1)
     off = grid.flatten(1).transpose(0, 1).contiguous().float()     # (n, 2)
     p = prefix + "pos."
-    x = F.linear(off, sd[p + "pos_proj.weight"], sd[p + "pos_proj.bias"])
+    x = F.linear(off.to(sd[p + "pos_proj.weight"].device), sd[p + "pos_proj.weight"], sd[p + "pos_proj.bias"])
     for name in ("pos1", "pos2", "pos3"):
         d = x.shape[-1]
         x = F.layer_norm(x, (d,), sd[p + name + ".0.weight"], sd[p + name + ".0.bias"], 1e-5)

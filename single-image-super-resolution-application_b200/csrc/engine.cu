@@ -713,9 +713,10 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
       fs = FfnStats{ws.cavg, ws.cmax, ws.part_sum, ws.part_max, round_up(f.H, wn), round_up(f.W, wn)};
       fsp = &fs;
     }
-    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_mma, bw.fc2.tm, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, fsp, h->num_sms, f.st));
+    bf16* shadow = (need_shadow && fsp == nullptr) ? ws.xb0 : nullptr;      // emitted by the kernel's statistics warp
+    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_mma, bw.fc2.tm, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, fsp, shadow, h->num_sms, f.st));
     if (fsp != nullptr) f.stats_nparts = ffn_tiles_per_image(f.H, f.W);
-    if (need_shadow) LAUNCH("cast_shadow", 1, launch_cast_rows_bf16(xout, ws.xb0, f.N, f.st));
+    if (need_shadow && shadow == nullptr) LAUNCH("cast_shadow", 1, launch_cast_rows_bf16(xout, ws.xb0, f.N, f.st));
   } else {
     LAUNCH("dwconv5", 1, launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, h->num_sms, f.st));
     // fc2 + norm2 + residual (:704)

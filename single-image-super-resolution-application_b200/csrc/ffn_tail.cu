@@ -55,6 +55,7 @@ struct Params {
   float* cavg; float* cmax;                  // per pixel channel mean / max, [B*H*W]
   float* part_sum; float* part_max;          // per tile per channel: reflect-weighted sum / max over the tile's pixels, [total][180]
   int Hp, Wp;                                // reflect-padded size of the NEXT block's window grid
+  bf16* shadow;                              // optional bf16 copy of the updated stream [B*H*W][192] (pads 0) for the RHTB conv that follows (:934)
 };
 __device__ __forceinline__ int reflect_mult(int i, int n, int np) { return 1 + ((i >= 2 * (n - 1) - (np - 1) && i <= n - 2) ? 1 : 0); }
 
@@ -91,6 +92,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
   float2* s_part2 = reinterpret_cast<float2*>(sp + kOffPart2);
   float* s_mult = reinterpret_cast<float*>(sp + kOffMult);
   const bool want_stats = p.cavg != nullptr;
+  const bool want_shadow = p.shadow != nullptr;
   const uint32_t bar0 = sb + kOffBars;
   auto halo_full = [&](int h) { return bar0 + 8u * h; };
   auto halo_empty = [&](int h) { return bar0 + 8u * (2 + h); };
@@ -222,6 +224,30 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         }
         __syncwarp();                                       // s_mult is rewritten for the next tile
       }
+    } else if (want_shadow) {
+      // the last block of a layer: no statistics are wanted, the warp converts every finished box to bf16 instead (16-byte chunks of 8
+      // channels straight to global), which used to be a separate pass over the stream (cast_rows_bf16)
+      uint32_t u = 0;
+      for (int t = blockIdx.x; t < p.total; t += gridDim.x) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        for (int j = 0; j < 6; ++j, ++u) {
+          const int s = (int)(u % kNBox);
+          mbar_wait(out_bar(s), (u / kNBox) & 1u);
+          const uint8_t* box = sp + kOffBox + s * kBoxBytes;
+#pragma unroll 4
+          for (int i = lane; i < 512; i += 32) {            // 128 pixels x 4 chunks of 8 channels
+            const int rr = i >> 2, c8 = i & 3;
+            const int y = y0 + (rr >> 4), x = x0 + (rr & 15);
+            const float4 v0 = *reinterpret_cast<const float4*>(box + rr * 128 + (((uint32_t)(2 * c8) ^ (uint32_t)(rr & 7)) << 4));
+            const float4 v1 = *reinterpret_cast<const float4*>(box + rr * 128 + (((uint32_t)(2 * c8 + 1) ^ (uint32_t)(rr & 7)) << 4));
+            if (y < p.H && x < p.W)
+              *reinterpret_cast<uint4*>(p.shadow + (((long long)b * p.H + y) * p.W + x) * kCp + 32 * j + 8 * c8) =
+                  make_uint4(pack_bf16x2(v0.x, v0.y), pack_bf16x2(v0.z, v0.w), pack_bf16x2(v1.x, v1.y), pack_bf16x2(v1.z, v1.w));
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(red_done(s));
+        }
+      }
     }
   } else if (warp == 3) {
     if (lane == 0) {
@@ -243,7 +269,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
             const uint32_t need = u_prep - (uint32_t)kNBox + 2u;
             while (u_store < need && u_store < u_prep) store_one();
             tma_wait_read1();                              // bulk groups retire in order: store #(u_prep - kNBox) has left the box
-            if (want_stats) mbar_wait(red_done(s), ((u_prep / kNBox) - 1u) & 1u);   // ... and the statistics warp has read it
+            if (want_stats || want_shadow) mbar_wait(red_done(s), ((u_prep / kNBox) - 1u) & 1u);   // ... and the statistics warp has read it
           }
           c0s[s] = 32 * j; r0s[s] = x0; r1s[s] = y0; r2s[s] = b;
           mbar_expect_tx(in_bar(s), kBoxBytes);
@@ -467,7 +493,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
 // h1: bf16 [B,H,W,384]; dw_tbl_mma: depthwise taps as B-fragment words + fp32 bias row (launch_pack_dw_mma); fc2 packed weights tensor
 // map (box {64, 192}); x: fp32 residual stream [B,H,W,180], updated in place
 int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
-                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st) {
+                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, bf16* shadow, int num_sms, cudaStream_t st) {
   static unsigned long long configured = 0;
   if (ensure_dynamic_smem(ffn_tail_kernel, kSmemBytes, &configured)) return 1;
   Params p;
@@ -478,6 +504,7 @@ int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMa
   p.total = (int)total;
   p.bias = b2; p.gamma = gamma; p.beta = beta;
   p.cavg = p.cmax = p.part_sum = p.part_max = nullptr; p.Hp = H; p.Wp = W;
+  p.shadow = stats == nullptr ? shadow : nullptr;          // the statistics warp does one or the other
   if (stats != nullptr) { p.cavg = stats->cavg; p.cmax = stats->cmax; p.part_sum = stats->part_sum; p.part_max = stats->part_max; p.Hp = stats->Hp; p.Wp = stats->Wp; }
   CUtensorMap tm_h1, tm_x, tm_dw;
   if (make_tmap_2d_plain(&tm_dw, dw_tbl_mma, 4, kDwRow, kHidp, (uint64_t)kDwRow * 4, kDwRow, 64)) return 1;

@@ -28,8 +28,9 @@ inline int ffn_tiles_per_image(int H, int W) { return ((H + 7) / 8) * ((W + 15) 
 // dw_tbl_mma (launch_pack_dw_mma from the fp32 [26][384] tap-major table): the depthwise taps as B-fragment words of the tensor-core
 // conv, [384 channels][28 words]: bf16(w) in the low (c even) / high (c odd) half in MMA pairing order, word 26 = fp32 bias bits (pack.cu)
 int launch_pack_dw_mma(const float* dw_tbl, uint32_t* out, cudaStream_t st);
+// shadow (only without stats): bf16 copy [B*H*W][192] of the updated stream, written by the kernel's statistics warp
 int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
-                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, int num_sms, cudaStream_t st);
+                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, bf16* shadow, int num_sms, cudaStream_t st);
 // proj_fc1.cu: proj + norm1 + residual chained with fc1 + GELU (the bf16 copy of the stream stays in shared memory); tm_wp = packed proj
 // weights (box {64, 192}), w1 = packed fc1 weights bf16 [384][192], res / xout fp32 [N][180], h1 bf16 [N][384]
 int launch_proj_fc1(const bf16* outsc, const CUtensorMap& tm_wp, const float* bp, const float* gamma, const float* beta, const float* res,
