@@ -92,6 +92,7 @@ struct HitsirHandle {
   int num_sms = 148;
   bool simt = false;
   bool projfc1_fused = false;     // HITSIR_PROJFC1=fused: proj + fc1 chained in one kernel (proj_fc1.cu; slower than the two GEMM launches so far)
+  bool b_streamed = false;        // HITSIR_GEMMW=streamed: linears re-load their weight tile per 128-token tile (A/B switch)
   bool no_epilogue_stats = false; // HITSIR_STATS=kernel: always compute the casa statistics with the stand-alone sca_stats pass
   bool ffn_unfused = false;       // HITSIR_FFN=unfused: separate dwconv5 and fc2 kernels for every block
   bool scc_gram_only = false;     // HITSIR_SCC=gram: use the Gram-matrix kernel (scc_umma.cu) for every window size
@@ -605,6 +606,8 @@ int run_gemm(Fwd& f, const char* cat, const GemmW& w, GemmParams& p, const CUten
 int linear(Fwd& f, const char* cat, const GemmW& w, const bf16* A, long long M, GemmParams& p) {
   p.conv = 0; p.M = (int)M; p.m_tiles = (int)cdiv64(M, 128);
   p.A = A; p.lda = w.K;
+  p.b_resident = f.h->b_streamed ? 0 : 1;                  // honoured by the TMA kernel when the weight tile fits next to the A ring
+
   CUtensorMap maps[5];
   const bool tma = tma_epilogue(f.h, w, p);
   if (!f.h->simt) {
@@ -914,6 +917,8 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
   h->no_epilogue_stats = env5 && strcmp(env5, "kernel") == 0;
   const char* env7 = getenv("HITSIR_PROJFC1");
   h->projfc1_fused = env7 && strcmp(env7, "fused") == 0;
+  const char* env8 = getenv("HITSIR_GEMMW");
+  h->b_streamed = env8 && strcmp(env8, "streamed") == 0;
   const char* env4 = getenv("HITSIR_FFN");
   h->ffn_unfused = env4 && strcmp(env4, "unfused") == 0;
   const char* env3 = getenv("HITSIR_SCC");

@@ -28,6 +28,7 @@ struct GemmParams {
   int tiles_x, tiles_y;
   int m_tiles, n_tiles;
   int num_kb;        // K / 64
+  int b_resident;    // linear, K <= 192, grid % n_tiles == 0: the CTA's weight tile is loaded once and stays in shared memory (umma_gemm_tma.cu)
   int cblocks;       // conv: Cin_pad / 64
   // epilogue
   int epi, act;

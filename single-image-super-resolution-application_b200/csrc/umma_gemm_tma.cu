@@ -100,7 +100,8 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * S + 2 + s); };
   auto in_bar = [&](int s) { return bar0 + 8u * (2 * S + 4 + s); };              // DMA -> epilogue: box s usable (residual landed / free)
   auto out_bar = [&](int s) { return bar0 + 8u * (2 * S + 4 + kNBox + s); };     // epilogue -> DMA: box s written
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + 2 * kNBox);
+  const uint32_t bres_full = bar0 + 8u * (2 * S + 4 + 2 * kNBox);                // resident-weights mode: the CTA's weight tile has landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * S + 4 + 2 * kNBox + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = p.m_tiles * p.n_tiles;
@@ -115,6 +116,7 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 4 * EQ); }
+    mbar_init(bres_full, 1);
     for (int s = 0; s < kNBox; ++s) {
       mbar_init(in_bar(s), 1);
       mbar_init(out_bar(s), s < nf ? 2 * EQ : 4 * EQ);   // warp-level arrivals; fp32 box (32 columns): half of the slices; bf16 box (64): all
@@ -143,6 +145,24 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (lane == 0) {
       // ===================== operand TMA producer =====================
       int stage = 0; uint32_t phase = 0;
+      if (p.b_resident) {
+        // Resident weights: every tile of this CTA has the same N tile (grid % n_tiles == 0), so its [BN x K] weight tile is fetched once
+        // into the head of the pipeline area and only the A k-blocks cycle through the ring behind it.  Re-streaming the weights for
+        // every 128-token tile made the linears L2->SM-bound (fc1: 240 KB per 128 tokens).
+        const int n_tile = (int)(blockIdx.x % (unsigned)p.n_tiles);
+        mbar_expect_tx(bres_full, p.num_kb * Cfg::kBBytes);
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(smem_base + kb * Cfg::kBBytes, &tmap_b, bres_full, kb * 64, n_tile * BN);
+        const uint32_t ring = smem_base + p.num_kb * Cfg::kBBytes;
+        for (int w = blockIdx.x; w < total; w += gridDim.x) {
+          const TileCoord t = tile_coord(p, w);
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            mbar_expect_tx(full_bar(stage), Cfg::kABytes);
+            tma_load_2d(ring + stage * Cfg::kABytes, &tmap_a, full_bar(stage), kb * 64, t.m_tile * 128);
+            if (++stage == S) { stage = 0; phase ^= 1u; }
+          }
+        }
+      } else
       for (int w = blockIdx.x; w < total; w += gridDim.x) {
         const TileCoord t = tile_coord(p, w);
         for (int kb = 0; kb < p.num_kb; ++kb) {
@@ -172,12 +192,13 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         mbar_wait(tempty_bar(as), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        if (p.b_resident && it == 0) mbar_wait(bres_full, 0u);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(full_bar(stage), phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::kStageBytes;
+          const uint32_t sa = p.b_resident ? smem_base + p.num_kb * Cfg::kBBytes + stage * Cfg::kABytes : smem_base + stage * Cfg::kStageBytes;
           const uint64_t adesc = umma_desc_sw128(sa);
-          const uint64_t bdesc = umma_desc_sw128(sa + Cfg::kABytes);
+          const uint64_t bdesc = umma_desc_sw128(p.b_resident ? smem_base + kb * Cfg::kBBytes : sa + Cfg::kABytes);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
@@ -417,8 +438,11 @@ static int launch_tma_bn(const GemmParams& p, const CUtensorMap* maps, int num_s
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms ? total : num_sms;
   if (grid <= 0) return 0;
+  GemmParams q = p;
+  q.b_resident = (p.b_resident && !p.conv && grid % p.n_tiles == 0 &&
+                  p.num_kb * Cfg::kBBytes + Cfg::kStages * Cfg::kABytes <= Cfg::kPipeBytes) ? 1 : 0;
   if (p.n_tiles * BN > Cfg::kMaxCols) { set_error("launch_umma_gemm_tma: %d output columns exceed the staged-parameter limit %d", p.n_tiles * BN, Cfg::kMaxCols); return 1; }
-  umma_gemm_tma_kernel<BN, EQ><<<grid, 128 + 128 * EQ, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], p);
+  umma_gemm_tma_kernel<BN, EQ><<<grid, 128 + 128 * EQ, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], q);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
