@@ -125,3 +125,57 @@ class ShardedSR:
             return None
         tiles = [buf[(i % world) * per + i // world] for i in range(len(origins))]
         return stitch_tiles(tiles, origins, H, W, s)
+
+
+class PeerGather:
+    """All-gather of equal per-rank slices by peer-to-peer copies over NVLink instead of an NCCL kernel.
+
+    Every rank owns `slots` symmetric output buffers [world, *slice] (torch symmetric memory: the same allocation is mapped into every
+    peer's address space).  `start(y, slot)` enqueues, on a side stream, a device-side barrier (all ranks have released the slot), one
+    copy of this rank's slice into row `rank` of every rank's buffer, and a second barrier (every peer's row has landed here); the
+    caller's stream only waits for it in `wait(slot)`.  A gather therefore overlaps the next forward pass -- the copies are plain
+    device-to-device transfers that need no SMs of the persistent compute kernels, whereas an NCCL all-gather kernel competes with them
+    for SMs -- which is what keeps 8-GPU weak scaling at the 1-GPU step time.  NVLink/NVSwitch only (same node); construct it
+    collectively on every rank of the group."""
+
+    def __init__(self, slice_shape, dtype, device, group=None, slots: int = 2):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        name = self.group.group_name
+        try:                                                    # older torch releases want the group opted in explicitly
+            if not symm_mem.is_symm_mem_enabled_for_group(name):
+                symm_mem.enable_symm_mem_for_group(name)
+        except Exception:
+            pass
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.slice_shape = tuple(slice_shape)
+        self.full_shape = (self.world,) + self.slice_shape
+        self.dtype = dtype
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.bufs, self.hdls, self.peers = [], [], []
+        for _ in range(slots):
+            buf = symm_mem.empty(self.full_shape, dtype=dtype, device=self.device)
+            hdl = symm_mem.rendezvous(buf, self.group)
+            self.bufs.append(buf)
+            self.hdls.append(hdl)
+            self.peers.append([hdl.get_buffer(p, self.full_shape, dtype) for p in range(self.world)])
+
+    def start(self, y_local: torch.Tensor, slot: int) -> None:
+        assert tuple(y_local.shape) == self.slice_shape and y_local.dtype == self.dtype
+        y_local = y_local.contiguous()
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))      # y_local is ready; this rank no longer reads the slot
+        with torch.cuda.stream(self.stream):
+            self.hdls[slot].barrier(channel=0)
+            for k in range(self.world):                                       # start with the neighbour: spreads the load over the switch
+                p = (self.rank + k) % self.world
+                self.peers[slot][p][self.rank].copy_(y_local, non_blocking=True)
+            self.hdls[slot].barrier(channel=1)
+        y_local.record_stream(self.stream)
+
+    def wait(self, slot: int) -> torch.Tensor:
+        """Makes the current stream wait for the gather started on `slot`; returns the [world, *slice] buffer (valid until the slot's
+        next `start`)."""
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        return self.bufs[slot]
