@@ -50,6 +50,7 @@ struct BlockW {
   GemmW proj, fc1, fc2;
   float *dw_w = nullptr, *dw_b = nullptr;
   uint32_t* dw_mma = nullptr;
+  uint8_t* w2_img = nullptr;
 };
 
 struct UaPack {
@@ -400,6 +401,9 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
       if (launch_pack_tapmajor(P(h, p + ".mlp.dwconv.depthwise_conv.0.bias"), bw.dw_b, kHid, 1, kHidp, st)) return 1;
       if (dev_alloc(h, &bw.dw_mma, 28 * kHidp)) return 1;
       if (launch_pack_dw_mma(bw.dw_w, bw.dw_mma, st)) return 1;
+      if (bw.fc2.Npad != 192 || bw.fc2.K != kHidp) { set_error("fc2 packing %d x %d is not the 192 x 384 the FFN tail expects", bw.fc2.Npad, bw.fc2.K); return 1; }
+      if (dev_alloc(h, &bw.w2_img, (size_t)6 * 192 * 128)) return 1;
+      if (launch_pack_w2_image(bw.fc2.w, bw.w2_img, st)) return 1;
     }
     if (make_gemm_w(h, &h->layer_conv[i], "layers." + std::to_string(i) + ".conv", C, C, 9, st)) return 1;
   }
@@ -717,7 +721,7 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
       fsp = &fs;
     }
     bf16* shadow = (need_shadow && fsp == nullptr) ? ws.xb0 : nullptr;      // emitted by the kernel's statistics warp
-    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_mma, bw.fc2.tm, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, fsp, shadow, h->num_sms, f.st));
+    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_mma, bw.w2_img, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, fsp, shadow, h->num_sms, f.st));
     if (fsp != nullptr) f.stats_nparts = ffn_tiles_per_image(f.H, f.W);
     if (need_shadow && shadow == nullptr) LAUNCH("cast_shadow", 1, launch_cast_rows_bf16(xout, ws.xb0, f.N, f.st));
   } else {

@@ -55,6 +55,8 @@ struct Params {
   float* cavg; float* cmax;                  // per pixel channel mean / max, [B*H*W]
   float* part_sum; float* part_max;          // per tile per channel: reflect-weighted sum / max over the tile's pixels, [total][180]
   int Hp, Wp;                                // reflect-padded size of the NEXT block's window grid
+  const uint32_t* dw_tbl;                    // tap rows [384][28] (launch_pack_dw_mma)
+  const uint8_t* w2_img;                     // fc2 weights as six SWIZZLE_128B operand images [192 rows x 64 k] (launch_pack_w2_image)
   bf16* shadow;                              // optional bf16 copy of the updated stream [B*H*W][192] (pads 0) for the RHTB conv that follows (:934)
 };
 __device__ __forceinline__ int reflect_mult(int i, int n, int np) { return 1 + ((i >= 2 * (n - 1) - (np - 1) && i <= n - 2) ? 1 : 0); }
@@ -80,8 +82,7 @@ __device__ __forceinline__ void ldmatrix_x2(uint32_t addr, uint32_t& r0, uint32_
 __device__ __forceinline__ void epi_bar_sync(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 
 __global__ void __launch_bounds__(640, 1)
-ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_dw, const __grid_constant__ CUtensorMap tm_w,
-                const __grid_constant__ CUtensorMap tm_x, const Params p) {
+ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant__ CUtensorMap tm_x, const Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sp = smem_raw + (sb - smem_u32(smem_raw));
@@ -108,7 +109,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sp + kOffBars + kNumBars * 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_h1); tma_prefetch_desc(&tm_dw); tma_prefetch_desc(&tm_w); tma_prefetch_desc(&tm_x); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tm_h1); tma_prefetch_desc(&tm_x); }
   if (warp == 1 && lane == 0) {
     for (int h = 0; h < 2; ++h) {
       mbar_init(halo_full(h), 1); mbar_init(halo_empty(h), 16);
@@ -148,10 +149,10 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
           mbar_wait(halo_empty(h), (u & 1u) ^ 1u);
           mbar_expect_tx(halo_full(h), kHalo + kDwTbl);
           tma_load_4d(sb + kOffHalo + h * kHaloStage, &tm_h1, halo_full(h), k * 64, x0 - 2, y0 - 2, b);
-          tma_load_2d(sb + kOffHalo + h * kHaloStage + kHalo, &tm_dw, halo_full(h), 0, k * 64);
+          bulk_load(sb + kOffHalo + h * kHaloStage + kHalo, p.dw_tbl + (size_t)k * (kDwTbl / 4), kDwTbl, halo_full(h));   // 64 contiguous tap rows
           mbar_wait(w_empty(h), (u & 1u) ^ 1u);
           mbar_expect_tx(w_full(h), kWStage);
-          tma_load_2d(sb + kOffWs + h * kWStage, &tm_w, w_full(h), k * 64, 0);
+          bulk_load(sb + kOffWs + h * kWStage, p.w2_img + (size_t)k * kWStage, kWStage, w_full(h));   // pre-swizzled operand image: one request, not 192 rows
         }
       }
     }
@@ -490,9 +491,9 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
 
 }  // namespace
 
-// h1: bf16 [B,H,W,384]; dw_tbl_mma: depthwise taps as B-fragment words + fp32 bias row (launch_pack_dw_mma); fc2 packed weights tensor
-// map (box {64, 192}); x: fp32 residual stream [B,H,W,180], updated in place
-int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
+// h1: bf16 [B,H,W,384]; dw_tbl_mma: depthwise tap rows (launch_pack_dw_mma); w2_img: fc2 operand images (launch_pack_w2_image);
+// x: fp32 residual stream [B,H,W,180], updated in place
+int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const uint8_t* w2_img, const float* b2, const float* gamma,
                     const float* beta, float* x, int B, int H, int W, const FfnStats* stats, bf16* shadow, int num_sms, cudaStream_t st) {
   static unsigned long long configured = 0;
   if (ensure_dynamic_smem(ffn_tail_kernel, kSmemBytes, &configured)) return 1;
@@ -506,12 +507,12 @@ int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMa
   p.cavg = p.cmax = p.part_sum = p.part_max = nullptr; p.Hp = H; p.Wp = W;
   p.shadow = stats == nullptr ? shadow : nullptr;          // the statistics warp does one or the other
   if (stats != nullptr) { p.cavg = stats->cavg; p.cmax = stats->cmax; p.part_sum = stats->part_sum; p.part_max = stats->part_max; p.Hp = stats->Hp; p.Wp = stats->Wp; }
-  CUtensorMap tm_h1, tm_x, tm_dw;
-  if (make_tmap_2d_plain(&tm_dw, dw_tbl_mma, 4, kDwRow, kHidp, (uint64_t)kDwRow * 4, kDwRow, 64)) return 1;
+  p.dw_tbl = dw_tbl_mma; p.w2_img = w2_img;
+  CUtensorMap tm_h1, tm_x;
   if (make_tmap_nhwc(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH)) return 1;               // SWIZZLE_128B halo boxes, zero fill outside the image
   if (make_tmap_nhwc_t(&tm_x, x, 4, B, H, W, kC, kC, 32, 16, 8)) return 1;
   const int grid = p.total < num_sms ? p.total : num_sms;
-  ffn_tail_kernel<<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_dw, tm_w2, tm_x, p);
+  ffn_tail_kernel<<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_x, p);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

@@ -29,7 +29,10 @@ inline int ffn_tiles_per_image(int H, int W) { return ((H + 7) / 8) * ((W + 15) 
 // conv, [384 channels][28 words]: bf16(w) in the low (c even) / high (c odd) half in MMA pairing order, word 26 = fp32 bias bits (pack.cu)
 int launch_pack_dw_mma(const float* dw_tbl, uint32_t* out, cudaStream_t st);
 // shadow (only without stats): bf16 copy [B*H*W][192] of the updated stream, written by the kernel's statistics warp
-int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const CUtensorMap& tm_w2, const float* b2, const float* gamma,
+// w2_img (launch_pack_w2_image): the packed fc2 weights [192][384] re-laid as six contiguous SWIZZLE_128B operand images [192 rows x 64 k]
+// (24 KB each), so that a slice is one bulk copy instead of 192 TMA rows
+int launch_pack_w2_image(const bf16* w2_packed, uint8_t* img, cudaStream_t st);
+int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const uint8_t* w2_img, const float* b2, const float* gamma,
                     const float* beta, float* x, int B, int H, int W, const FfnStats* stats, bf16* shadow, int num_sms, cudaStream_t st);
 // proj_fc1.cu: proj + norm1 + residual chained with fc1 + GELU (the bf16 copy of the stream stays in shared memory); tm_wp = packed proj
 // weights (box {64, 192}), w1 = packed fc1 weights bf16 [384][192], res / xout fp32 [N][180], h1 bf16 [N][384]

@@ -100,6 +100,16 @@ __global__ void pack_tapmajor_kernel(const float* __restrict__ w, float* __restr
   }
 }
 
+// fc2 weights [192 rows][384 k] bf16 (K-major) -> six operand images of [192 rows x 64 k]: the byte image a SWIZZLE_128B TMA box would
+// leave in shared memory (row r = 128 bytes, 16-byte chunk c stored at chunk position c ^ (r & 7)); thread = one 16-byte chunk
+__global__ void pack_w2_image_kernel(const bf16* __restrict__ w, uint8_t* __restrict__ img) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 6 * 192 * 8) return;
+  const int c = idx & 7, r = (idx >> 3) % 192, k = idx / (192 * 8);
+  const uint4 v = *reinterpret_cast<const uint4*>(w + (size_t)r * kHidp + k * 64 + c * 8);
+  *reinterpret_cast<uint4*>(img + (size_t)k * (192 * 128) + r * 128 + ((c ^ (r & 7)) << 4)) = v;
+}
+
 // depthwise taps as MMA B-fragment words (ffn_tail.cu): one row of 28 words per channel, bf16(w) in the half selected by the channel parity,
 // in the order in which the 13 MMAs of an output row pair the taps: words 4 ky + dx (dx = 0..3), 20 + ky for the taps (ky, 4) with ky < 4,
 // 24 = tap (4,4), 26 = the bias as fp32 bits, 25 and 27 = 0.  tbl = fp32 tap-major table [26][384] (row 25 = bias).
@@ -198,6 +208,11 @@ int launch_pack_firstconv(const float* w, const float* b, bf16* wp, float* bp, i
 }
 int launch_pack_tapmajor(const float* w, float* out, int C, int taps, int Cpad, cudaStream_t st) {
   pack_tapmajor_kernel<<<grid_for((long long)taps * Cpad, 256), 256, 0, st>>>(w, out, C, taps, Cpad);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pack_w2_image(const bf16* w2_packed, uint8_t* img, cudaStream_t st) {
+  pack_w2_image_kernel<<<grid_for(6 * 192 * 8, 256), 256, 0, st>>>(w2_packed, img);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
