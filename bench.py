@@ -348,6 +348,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # all the host threads this process may use: torchrun exports OMP_NUM_THREADS=1, which would make the reference arm single-threaded
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except (AttributeError, OSError):
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     flags, up, scale, B, H, W, desc = WORKLOADS[args.workload]
     total = args.steps + args.warmup
     hw = (H, W) if total <= 3 else ((128, 128) if total <= 12 else (64, 64))
