@@ -114,6 +114,11 @@ HITSIR_API int hitsir_forward_host(HitsirHandle* h, const float* host_x, float* 
 HITSIR_API int hitsir_forward_u8(HitsirHandle* h, const uint8_t* x_hwc, uint8_t* y_hwc, int B, int H, int W,
                       float* dev_x, float* dev_y, void* workspace, size_t workspace_bytes, void* stream);
 
+/* The exit conversion alone: clip(0,1) (experiments/experiment.py:746-748) and torchvision's to_pil_image (value * 255, truncated) of
+ * an fp32 NCHW batch [B,C,H,W] into uint8 HWC [B,H,W,C], both on the device.  Used before the multi-GPU output gather: a quarter of
+ * the fp32 bytes cross NVLink.  Needs no handle; asynchronous on `stream`. */
+HITSIR_API int hitsir_f32nchw_to_u8hwc(const float* src, uint8_t* dst, int B, int C, int H, int W, void* stream);
+
 /* The evaluation metric around the path on the device (experiments/experiment.py:436-463, called per batch from :743-755): both fp32
  * NCHW batches [B,3,H,W] in [0,1] are converted to the Y channel of YCbCr exactly as utils/utils.py:170-186 does
  * (16/255 + (65.738 R + 129.057 G + 25.064 B) / 256, fp32), `sr` clipped to [0,1] first when clip_sr != 0 (experiment.py:746-748),
@@ -132,6 +137,19 @@ HITSIR_API int hitsir_psnr_y(const float* sr, const float* hr, int B, int H, int
  * Pass name = NULL to clear. */
 HITSIR_API int hitsir_set_tap(HitsirHandle* h, const char* name, float* dst, int64_t dst_floats, int stop);
 
+/* Test hook standing in for a PyTorch forward PRE-hook that replaces a sub-module's input (nn.Module.register_forward_pre_hook):
+ * the next hitsir_forward calls overwrite the named activation with `src` (device, fp32, NHWC, [B*H*W, 180]) right before it is
+ * consumed.  Names: "block<i>.<j>.in" (the token stream entering HierarchicalTransformerBlock i.j, hit_sir_pro.py:676) and
+ * "fused" (the input of the reconstruction stage, :1313-1340).  Together with hitsir_set_tap it isolates one stage, which is how the
+ * index work (reflect padding :664-674, window partition / reverse :236-271, nearest upsampling :1331-1332, PixelShuffle :1024-1062)
+ * is checked bit for bit.  `src` must stay valid until cleared; pass name = NULL to clear. */
+HITSIR_API int hitsir_set_inject(HitsirHandle* h, const char* name, const float* src, int64_t src_floats);
+
+/* The pooled relative-position bias of SCC block (layer, block): `relative_position_bias` of hit_sir_pro.py:477-503, fp32
+ * [6 heads][L = w*w tokens][Lb = min(w,8)^2 pooled cells], as precomputed by hitsir_finalize_weights (the reference rebuilds it on
+ * every forward).  Copies `dst_floats` = 6*L*Lb floats to `dst` (host or device) on `stream`. */
+HITSIR_API int hitsir_get_bias_table(HitsirHandle* h, int layer, int block, float* dst, int64_t dst_floats, void* stream);
+
 /* Number of kernels the last hitsir_forward launched (bench.py's gpu_launches). */
 HITSIR_API int64_t hitsir_last_launch_count(const HitsirHandle* h);
 
@@ -142,7 +160,8 @@ HITSIR_API int hitsir_profile_enable(HitsirHandle* h, int on);
 HITSIR_API int hitsir_profile_num_categories(const HitsirHandle* h);
 HITSIR_API int hitsir_profile_get(HitsirHandle* h, int index, const char** name, double* total_ms, int64_t* launches);
 
-/* "umma" (tcgen05 path, default) or "simt" (cross-check kernels); also via env HITSIR_GEMM. */
+/* "umma" (tcgen05 path with TMA-staged epilogues, default) or "umma_direct" (same mainloop, per-row global stores).  A test build with
+ * -DHITSIR_AB_PATHS additionally accepts "simt" (fp32 cross-check kernels); the product library has no other backend. */
 HITSIR_API int hitsir_set_gemm_backend(HitsirHandle* h, const char* backend);
 
 HITSIR_API const char* hitsir_last_error(void);

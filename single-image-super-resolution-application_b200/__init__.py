@@ -9,9 +9,9 @@ provides device memory, streams and `torch.distributed` plumbing.
 """
 from .hit_sir_pro import HiT_SIR, PRO_KWARGS  # noqa: F401
 from . import _capi  # noqa: F401
-from .sharding import ShardedSR, tile_plan, stitch_tiles  # noqa: F401
+from .sharding import ShardedSR, PeerGather, tile_plan, stitch_tiles  # noqa: F401
 from .host_pipeline import HostPipeline  # noqa: F401
-from .metrics import mse_y, psnr_y  # noqa: F401
+from .metrics import mse_y, psnr_y, to_uint8_hwc  # noqa: F401
 from .graphed import GraphedForward  # noqa: F401
 
-__all__ = ["HiT_SIR", "PRO_KWARGS", "ShardedSR", "tile_plan", "stitch_tiles", "HostPipeline", "mse_y", "psnr_y", "GraphedForward"]
+__all__ = ["HiT_SIR", "PRO_KWARGS", "ShardedSR", "tile_plan", "stitch_tiles", "HostPipeline", "mse_y", "psnr_y", "to_uint8_hwc", "GraphedForward"]

@@ -54,9 +54,12 @@ SYMBOLS = {
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "hitsir_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_size_t, C.c_void_p]),
+    "hitsir_f32nchw_to_u8hwc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "hitsir_psnr_y_scratch_doubles": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "hitsir_psnr_y": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "hitsir_set_tap": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64, C.c_int]),
+    "hitsir_set_inject": (C.c_int, [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int64]),
+    "hitsir_get_bias_table": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p]),
     "hitsir_last_launch_count": (C.c_int64, [C.c_void_p]),
     "hitsir_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "hitsir_profile_num_categories": (C.c_int, [C.c_void_p]),
@@ -76,7 +79,9 @@ class HitsirError(RuntimeError):
 
 
 def library_path() -> str:
-    return _build.LIB
+    """The in-tree product library.  HITSIR_B200_LIB names another build of the SAME sources (build.py variants for kernel
+    experiments and the -DHITSIR_AB_PATHS cross-check build used by tests); it is never a different backend."""
+    return os.environ.get("HITSIR_B200_LIB") or _build.LIB
 
 
 def load():
@@ -90,7 +95,7 @@ def load():
             f"{path} not found: build the CUDA library first (python __graft_entry__.py build, needs nvcc). "
             "hitsir_b200 has no CPU/PyTorch fallback for the forward pass.")
     stamp = os.path.join(_build.BUILD, "stamp.txt")
-    if os.path.exists(stamp) and os.path.isdir(_build.CSRC):
+    if path == _build.LIB and os.path.exists(stamp) and os.path.isdir(_build.CSRC):
         try:
             if open(stamp).read().strip() != _build._digest():
                 raise ImportError(f"{path} is older than its sources in {_build.CSRC}: rebuild (python __graft_entry__.py build)")

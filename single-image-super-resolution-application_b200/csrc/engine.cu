@@ -83,6 +83,13 @@ struct Tap {
   int stop = 0;
 };
 
+// test hook: replaces a named activation with caller data before it is consumed (a forward *pre*-hook that returns a new input)
+struct Inject {
+  std::string name;
+  const float* src = nullptr;
+  int64_t floats = 0;
+};
+
 }  // namespace hitsir
 
 using namespace hitsir;
@@ -91,6 +98,7 @@ struct HitsirHandle {
   HitsirConfig cfg;
   int device = 0;
   int num_sms = 148;
+  // A/B switches: only a test build (-DHITSIR_AB_PATHS, build.py --ab) can turn them on; the product has ONE path and they stay false
   bool simt = false;
   bool projfc1_fused = false;     // HITSIR_PROJFC1=fused: proj + fc1 chained in one kernel (proj_fc1.cu; slower than the two GEMM launches so far)
   bool b_streamed = false;        // HITSIR_GEMMW=streamed: linears re-load their weight tile per 128-token tile (A/B switch)
@@ -116,6 +124,7 @@ struct HitsirHandle {
   float mean[4] = {0, 0, 0, 0};
   // per-forward state
   Tap tap;
+  Inject inject;
   int64_t launches = 0;
   Prof prof;
 };
@@ -254,6 +263,7 @@ int validate_config(const HitsirConfig& c) {
   if (c.upsampler == HITSIR_UP_PIXELSHUFFLE) {
     const int s = c.upscale;
     if (!((s & (s - 1)) == 0 || s == 3) || s < 1) { set_error("scale %d is not supported. Supported scales: 2^n and 3.", s); return HITSIR_ERR_INVALID; }   // (:1042)
+    if (s > 4) { set_error("upsampler='pixelshuffle' with upscale %d is not implemented in this build (1, 2, 3, 4)", s); return HITSIR_ERR_UNSUPPORTED; }
   }
   if (c.upsampler == HITSIR_UP_PIXELSHUFFLEDIRECT && (c.upscale < 1 || c.upscale * c.upscale * c.in_chans > 256)) {
     set_error("pixelshuffledirect upscale %d not supported", c.upscale); return HITSIR_ERR_UNSUPPORTED;
@@ -565,6 +575,16 @@ int do_tap(Fwd& f, const char* name, const void* src, int is_bf16, int ld, long 
   return 0;
 }
 
+// `name` matches the pending injection: overwrite the fp32 rows [rows, 180] at `dst_f32` and/or the bf16 rows [rows, 192] at `dst_bf16`
+int do_inject(Fwd& f, const char* name, float* dst_f32, bf16* dst_bf16, long long rows) {
+  Inject& in = f.h->inject;
+  if (in.src == nullptr || in.name != name) return 0;
+  if (rows * kC != in.floats) { set_error("inject '%s' needs %lld floats, source has %lld", name, rows * kC, (long long)in.floats); return HITSIR_ERR_INVALID; }
+  if (dst_f32 != nullptr) HITSIR_CHECK(cudaMemcpyAsync(dst_f32, in.src, (size_t)rows * kC * sizeof(float), cudaMemcpyDeviceToDevice, f.st));
+  if (dst_bf16 != nullptr && launch_cast_rows_bf16(in.src, dst_bf16, rows, f.st)) return 1;
+  return 0;
+}
+
 #define RUN(expr) do { int _r = (expr); if (_r) return _r; } while (0)
 struct ProfScope {
   HitsirHandle* h; cudaStream_t st; int idx = -1;
@@ -601,7 +621,9 @@ bool tma_epilogue(const HitsirHandle* h, const GemmW& w, const GemmParams& p) {
 int run_gemm(Fwd& f, const char* cat, const GemmW& w, GemmParams& p, const CUtensorMap* maps, bool tma) {
   ProfScope ps(f.h, f.st, cat);
   f.h->launches++;
+#ifdef HITSIR_AB_PATHS
   if (f.h->simt) return launch_simt_gemm(w.BN, p, f.st);
+#endif
   if (tma) return launch_umma_gemm_tma(w.BN, p, maps, f.h->num_sms, f.st);
   return launch_umma_gemm(w.BN, p, maps[0], w.tm, f.h->num_sms, f.st);
 }
@@ -672,6 +694,13 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   g.w = w; g.base = bw.base; g.r = bw.r; g.L = w * w; g.Lb = bw.base * bw.base;
   g.nWy = g.pg.Hp / w; g.nWx = g.pg.Wp / w; g.parts = 1;
   const long long Np = (long long)f.B * g.pg.Hp * g.pg.Wp;
+  {
+    const Inject& in = h->inject;
+    if (in.src != nullptr && in.name == tn + ".in") {
+      RUN(do_inject(f, in.name.c_str(), xin, nullptr, f.N));
+      f.stats_nparts = 0;                                  // statistics delivered by the previous block no longer describe the stream
+    }
+  }
   if (c.is_channel_spatial_attn) {
     int nparts = f.stats_nparts;
     if (nparts == 0) {       // no producer epilogue delivered them (first block of a layer, unfused fallback): one pass over the stream
@@ -694,11 +723,14 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   TAP((tn + ".sccdbg").c_str(), ws.scc_dbg, 0, kSccDbgFloats, 1, kSccDbgFloats);
   TAPP((tn + ".scc").c_str(), ws.outsc, 1, kCp, f.N, kC);
   GemmParams p;
+#ifdef HITSIR_AB_PATHS
   if (!h->simt && !h->direct_epilogue && h->projfc1_fused && bw.proj.BN == 192 && bw.proj.K == 192 && bw.fc1.K == 192 && bw.fc1.Npad == 384) {
     // proj + norm1 + residual and fc1 + GELU in one kernel (:597, :700-703, :39-41)
     LAUNCH("proj_fc1", 1, launch_proj_fc1(ws.outsc, bw.proj.tm, bw.proj.b, bw.g1, bw.b1, xin, xout, bw.fc1.w, bw.fc1.b, ws.H1, f.N, h->num_sms, f.st));
     TAP((tn + ".attn").c_str(), xout, 0, kC, f.N, kC);
-  } else {
+  } else
+#endif
+  {
   // proj + norm1 + residual (:597, :700-703)
   base_params(p, bw.proj);
   p.epi = EPI_LN; p.n_real = kC; p.gamma = bw.g1; p.beta = bw.b1; p.res = xin; p.ldr = kC;
@@ -725,6 +757,7 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
     if (fsp != nullptr) f.stats_nparts = ffn_tiles_per_image(f.H, f.W);
     if (need_shadow && shadow == nullptr) LAUNCH("cast_shadow", 1, launch_cast_rows_bf16(xout, ws.xb0, f.N, f.st));
   } else {
+#ifdef HITSIR_AB_PATHS
     LAUNCH("dwconv5", 1, launch_dwconv5_gelu_add(ws.H1, bw.dw_w, bw.dw_b, ws.H2, f.B, f.H, f.W, h->num_sms, f.st));
     // fc2 + norm2 + residual (:704)
     base_params(p, bw.fc2);
@@ -732,6 +765,10 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
     p.out_f32 = xout; p.ldf = kC;
     if (need_shadow) { p.out_bf16 = ws.xb0; p.ldb = kCp; }
     RUN(linear(f, "gemm_fc2_ln", bw.fc2, ws.H2, f.N, p));
+#else
+    set_error("unfused FFN path is only available in the A/B test build (-DHITSIR_AB_PATHS)");
+    return HITSIR_ERR_UNSUPPORTED;
+#endif
   }
   TAP(tn.c_str(), xout, 0, kC, f.N, kC);
   return 0;
@@ -815,6 +852,7 @@ int forward_impl(Fwd& f, const float* x, float* y) {
     LAUNCH("fusion_add", 1, launch_add_to_bf16(CAB, ws.S, F, N, f.st));
     TAP("fused", F, 1, kCp, N, kC);
   }
+  RUN(do_inject(f, "fused", nullptr, F, N));
   // ---- reconstruction (:1313-1340)
   const int s = c.upscale;
   auto last_params = [&](GemmParams& q, const GemmW& w, int ps) {
@@ -915,6 +953,7 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
   h->device = dev;
   h->num_sms = prop.multiProcessorCount;
   if (cfg->in_chans == 3) { h->mean[0] = 0.485f; h->mean[1] = 0.456f; h->mean[2] = 0.4060f; }   // (:1128)
+#ifdef HITSIR_AB_PATHS
   const char* env = getenv("HITSIR_GEMM");
   h->simt = env && strcmp(env, "simt") == 0;
   const char* env5 = getenv("HITSIR_STATS");
@@ -929,6 +968,7 @@ HITSIR_API int hitsir_create(const HitsirConfig* cfg, HitsirHandle** out) {
   h->scc_gram_only = env3 && strcmp(env3, "gram") == 0;
   const char* env2 = getenv("HITSIR_EPILOGUE");
   h->direct_epilogue = env2 && strcmp(env2, "direct") == 0;
+#endif
   build_param_list(h);
   e = cudaMalloc(reinterpret_cast<void**>(&h->arena), h->arena_floats * sizeof(float));
   if (e != cudaSuccess) { set_error("cudaMalloc(param arena): %s", cudaGetErrorString(e)); delete h; return HITSIR_ERR_CUDA; }
@@ -1023,6 +1063,12 @@ HITSIR_API int hitsir_forward_u8(HitsirHandle* h, const uint8_t* x_hwc, uint8_t*
   return 0;
 }
 
+HITSIR_API int hitsir_f32nchw_to_u8hwc(const float* src, uint8_t* dst, int B, int C, int H, int W, void* stream) {
+  if (!src || !dst || B <= 0 || C <= 0 || H <= 0 || W <= 0) { set_error("hitsir_f32nchw_to_u8hwc: bad argument"); return HITSIR_ERR_INVALID; }
+  if (launch_f32nchw_to_u8hwc(src, dst, B, H, W, C, (cudaStream_t)stream)) return HITSIR_ERR_CUDA;
+  return 0;
+}
+
 HITSIR_API int64_t hitsir_psnr_y_scratch_doubles(int B, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0) return 0;
   return (int64_t)B * psnr_y_chunks(H, W);
@@ -1039,6 +1085,27 @@ HITSIR_API int hitsir_set_tap(HitsirHandle* h, const char* name, float* dst, int
   if (!h) { set_error("null handle"); return HITSIR_ERR_INVALID; }
   if (!name) { h->tap = Tap(); return 0; }
   h->tap.name = name; h->tap.dst = dst; h->tap.floats = dst_floats; h->tap.stop = stop;
+  return 0;
+}
+
+HITSIR_API int hitsir_set_inject(HitsirHandle* h, const char* name, const float* src, int64_t src_floats) {
+  if (!h) { set_error("null handle"); return HITSIR_ERR_INVALID; }
+  if (!name) { h->inject = Inject(); return 0; }
+  if (!src) { set_error("hitsir_set_inject: null source"); return HITSIR_ERR_INVALID; }
+  h->inject.name = name; h->inject.src = src; h->inject.floats = src_floats;
+  return 0;
+}
+
+HITSIR_API int hitsir_get_bias_table(HitsirHandle* h, int layer, int block, float* dst, int64_t dst_floats, void* stream) {
+  if (!h || !dst) { set_error("hitsir_get_bias_table: null argument"); return HITSIR_ERR_INVALID; }
+  if (!h->finalized) { set_error("hitsir_get_bias_table: weights not finalized"); return HITSIR_ERR_WEIGHTS; }
+  if (layer < 0 || layer >= (int)h->blocks.size() || block < 0 || block >= (int)h->blocks[layer].size()) {
+    set_error("hitsir_get_bias_table: no block %d.%d", layer, block); return HITSIR_ERR_INVALID;
+  }
+  const BlockW& bw = h->blocks[layer][block];
+  const int64_t n = (int64_t)kHeads * bw.win * bw.win * bw.base * bw.base;
+  if (dst_floats != n) { set_error("hitsir_get_bias_table: block %d.%d has %lld values (6 x L x Lb), destination %lld", layer, block, (long long)n, (long long)dst_floats); return HITSIR_ERR_INVALID; }
+  HITSIR_CHECK(cudaMemcpyAsync(dst, bw.bias_tbl, (size_t)n * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
   return 0;
 }
 
@@ -1069,8 +1136,10 @@ HITSIR_API int hitsir_set_gemm_backend(HitsirHandle* h, const char* backend) {
   if (!h || !backend) { set_error("null argument"); return HITSIR_ERR_INVALID; }
   if (strcmp(backend, "umma") == 0) { h->simt = false; h->direct_epilogue = false; }
   else if (strcmp(backend, "umma_direct") == 0) { h->simt = false; h->direct_epilogue = true; }
+#ifdef HITSIR_AB_PATHS
   else if (strcmp(backend, "simt") == 0) h->simt = true;
-  else { set_error("unknown gemm backend '%s' (umma|simt)", backend); return HITSIR_ERR_INVALID; }
+#endif
+  else { set_error("unknown gemm backend '%s' (umma | umma_direct; 'simt' only in the -DHITSIR_AB_PATHS test build)", backend); return HITSIR_ERR_INVALID; }
   return 0;
 }
 

@@ -73,6 +73,7 @@ __global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restr
   }
 }
 
+#ifdef HITSIR_AB_PATHS   // stand-alone depthwise path: A/B test build only (the product runs ffn_tail.cu)
 // h2 = h1 + gelu(dw5x5(h1) + b)   (ConvFFN middle, hit_sir_pro.py:42 with :15-17).
 // Persistent CTAs (one per SM, 16 warps) walk (16 x 32 pixel tile, 64-channel slice) work items.  One TMA box load stages the
 // (16+4) x (32+4) x 64 bf16 input patch (the conv's zero padding = TMA out-of-bounds fill) into one of two buffers while the
@@ -168,6 +169,8 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwconv5_kernel(const __grid_con
     __syncthreads();                                // every warp is done with `buf` before it is refilled (next iteration's issue)
   }
 }
+
+#endif  // HITSIR_AB_PATHS
 
 // thread = (output pixel, 16-byte chunk)
 __global__ void upsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
@@ -397,6 +400,7 @@ __global__ void qkv_build_kernel(const float* __restrict__ x, PadGeom g, bf16* _
   }
 }
 
+#ifdef HITSIR_AB_PATHS   // SIMT gate: A/B test build only
 // casa gate: CTA = (image b, padded row yp, run of 64 padded pixels); thread = pair of head-padded positions (2t, 2t+1);
 // an even position is never a pad, the odd one is a pad when (2t+1) % 16 == 15 (position 15 carries the constant 1).
 // The two 3x3 filters of a channel pair live in registers, the 3 x 66 window of both statistic maps in shared
@@ -474,6 +478,8 @@ __global__ void __launch_bounds__(96, 10) qkv_casa_kernel(const float* __restric
     }
   }
 }
+
+#endif  // HITSIR_AB_PATHS
 
 // ---------------------------------------------------------------------------------------------
 // casa gate on the tensor core.  The two Conv2d(1, C, 3) of SpatialChannelAttention (:345-347) are a K = 9 contraction per pixel
@@ -811,6 +817,7 @@ int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* 
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
+#ifdef HITSIR_AB_PATHS
 int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, bf16* h2, int B, int H, int W, int num_sms, cudaStream_t st) {
   const int smem = 2 * kDwTileBytes + 32;
   static unsigned long long configured = 0;
@@ -825,6 +832,7 @@ int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, b
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
+#endif
 int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st) {
   const long long total = (long long)B * 4 * H * W * (C / 8);
   upsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, out, B, H, W, C);
@@ -885,16 +893,19 @@ int launch_sca_mlp(const float* part_sum, const float* part_max, int nparts, Pad
 int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, const float* cmax, const float* s1, const float* s2, CasaW w, bf16* t,
                      cudaStream_t st) {
   if (casa) {
+#ifdef HITSIR_AB_PATHS
     static const bool simt = getenv("HITSIR_CASA") != nullptr && strcmp(getenv("HITSIR_CASA"), "simt") == 0;   // A/B switch: the SIMT gate
-    if (w.bfrag != nullptr && !simt) {
-      static unsigned long long configured = 0;
-      if (ensure_dynamic_smem(qkv_casa_mma_kernel, kMmaSmem, &configured)) return 1;
-      qkv_casa_mma_kernel<<<g.B * g.Hp, 128, kMmaSmem, st>>>(x, g, cavg, cmax, s1, s2, w.bfrag, t);
+    if (simt || w.bfrag == nullptr) {
+      const int runs = (g.Wp + kQkvRun - 1) / kQkvRun;
+      qkv_casa_kernel<<<g.B * g.Hp * runs, 96, 0, st>>>(x, g, cavg, cmax, s1, s2, w, t, runs);
       HITSIR_CHECK(cudaGetLastError());
       return 0;
     }
-    const int runs = (g.Wp + kQkvRun - 1) / kQkvRun;
-    qkv_casa_kernel<<<g.B * g.Hp * runs, 96, 0, st>>>(x, g, cavg, cmax, s1, s2, w, t, runs);
+#endif
+    if (w.bfrag == nullptr) { set_error("launch_qkv_build: casa B fragments were not packed"); return 1; }
+    static unsigned long long configured = 0;
+    if (ensure_dynamic_smem(qkv_casa_mma_kernel, kMmaSmem, &configured)) return 1;
+    qkv_casa_mma_kernel<<<g.B * g.Hp, 128, kMmaSmem, st>>>(x, g, cavg, cmax, s1, s2, w.bfrag, t);
     HITSIR_CHECK(cudaGetLastError());
     return 0;
   }

@@ -168,7 +168,6 @@ __global__ void pos_table_kernel(PosW w, int win, float* __restrict__ tbl) {
 __global__ void pooled_bias_kernel(const float* __restrict__ tbl, int win, int base, float* __restrict__ out) {
   const int r = win / base, L = win * win, Lb = base * base, side = 2 * win - 1;
   const long long total = (long long)kHeads * L * Lb;
-  const float inv = 1.0f / (float)(r * r);
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int cell = (int)(idx % Lb); const long long t = idx / Lb; const int l = (int)(t % L); const int h = (int)(t / L);
     const int yl = l / win, xl = l - yl * win;
@@ -179,7 +178,7 @@ __global__ void pooled_bias_kernel(const float* __restrict__ tbl, int win, int b
         const int ym = cy * r + i, xm = cx * r + j;
         s += tbl[((yl - ym + win - 1) * side + (xl - xm + win - 1)) * kHeads + h];
       }
-    out[idx] = s * inv;
+    out[idx] = s / (float)(r * r);          // a true division, like the reference's .mean(-1) (:501): a constant table stays exact
   }
 }
 

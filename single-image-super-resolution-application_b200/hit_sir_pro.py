@@ -15,6 +15,7 @@ from __future__ import annotations
 import ctypes
 import math
 import warnings
+import weakref
 from typing import Dict, Optional
 
 import torch
@@ -36,6 +37,37 @@ PRO_KWARGS = dict(embed_dim=180, base_win_size=[8, 8], depths=[6] * 6, num_heads
 def _trunc_normal_(t: torch.Tensor, std: float = .02):
     # utils/arch_util.py:138-199 == timm trunc_normal_ (a=-2, b=2 in absolute units)
     return nn.init.trunc_normal_(t, mean=0., std=std, a=-2., b=2.)
+
+
+def _destroy_handles(handles: dict) -> None:
+    try:
+        lib = _capi.load()
+        for h in handles.values():
+            lib.hitsir_destroy(h)
+    except Exception:
+        pass
+    handles.clear()
+
+
+class _NativeState:
+    """Everything the module owns on the native side (C handles with their packed weights, the sync key, the cached workspace).
+    It is not part of the module's value: `copy.deepcopy(model)` and pickling (`torch.save(model)`, EMA copies, DataLoader workers)
+    give the copy a fresh, empty state that is re-created lazily on its first forward, exactly like a reference module that carries
+    no native state at all.  Shallow replicas (`nn.DataParallel.replicate`, `copy.copy`) share this object; the handles are released
+    when the LAST module referring to it is collected (weakref.finalize on the state object, not `__del__` on the module)."""
+
+    def __init__(self):
+        self.handles: Dict[int, ctypes.c_void_p] = {}
+        self.synced: Dict[int, tuple] = {}
+        self.workspaces: Dict[tuple, torch.Tensor] = {}
+        self.params = None                      # cached parameter list for the cheap weights key
+        weakref.finalize(self, _destroy_handles, self.handles)
+
+    def __deepcopy__(self, memo):
+        return _NativeState()
+
+    def __reduce__(self):
+        return (_NativeState, ())
 
 
 # ----------------------------------------------------------------------------------------------
@@ -219,6 +251,8 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
             raise NotImplementedError("hitsir_b200: patch_norm=False is not implemented")
         if resi_connection != '1conv':
             raise NotImplementedError("hitsir_b200: resi_connection='3conv' is not implemented")
+        if upsampler == 'pixelshuffle' and (upscale & (upscale - 1)) == 0 and upscale > 4:
+            raise NotImplementedError(f"hitsir_b200: upsampler='pixelshuffle' with upscale={upscale} is not implemented (1, 2, 3, 4)")
         if embed_dim != 180 or any(h != 6 for h in num_heads) or float(mlp_ratio) != 2.0:
             raise NotImplementedError("hitsir_b200 implements the HiT-SIR-pro width: embed_dim=180, num_heads=6, mlp_ratio=2 "
                                       f"(got embed_dim={embed_dim}, num_heads={num_heads}, mlp_ratio={mlp_ratio})")
@@ -254,10 +288,10 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
             self.conv_last = nn.Conv2d(num_feat, in_chans, 3, 1, 1)
         self.apply(self._init_weights)
 
-        # native state (never part of state_dict)
-        self._handles: Dict[int, ctypes.c_void_p] = {}
-        self._synced: Dict[int, tuple] = {}
-        self._workspaces: Dict[tuple, torch.Tensor] = {}
+        # native state (never part of state_dict, never copied or pickled: see _NativeState)
+        self._native = _NativeState()
+        self._forced_workspace: Optional[torch.Tensor] = None      # set by GraphedForward around its capture
+        self._inject_src: Optional[torch.Tensor] = None
         self._warned_grad = False
         self.last_launch_count = 0
 
@@ -297,7 +331,7 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
 
     def _handle(self, device: torch.device) -> ctypes.c_void_p:
         idx = device.index if device.index is not None else torch.cuda.current_device()
-        h = self._handles.get(idx)
+        h = self._native.handles.get(idx)
         if h is None:
             lib = _capi.load()
             cfg = self._config()
@@ -305,7 +339,7 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
             with torch.cuda.device(idx):
                 _capi.check(lib.hitsir_create(ctypes.byref(cfg), ctypes.byref(out)))
             h = out
-            self._handles[idx] = h
+            self._native.handles[idx] = h
             # the C side and this module must agree on the state_dict key set
             names = {lib.hitsir_param_name(h, i).decode() for i in range(lib.hitsir_num_params(h))}
             mine = set(self.state_dict().keys())
@@ -315,20 +349,32 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
         return h
 
     def _weights_key(self):
-        return tuple(p._version for p in self.parameters())
+        # in-place updates (optimizer steps, load_state_dict's copy_) bump Tensor._version; the parameter list itself is cached
+        # because walking the 1650-entry module tree costs more than a small forward (invalidated by _apply / refresh_weights)
+        ns = self._native
+        if ns.params is None:
+            ns.params = list(self.parameters())
+        return tuple([p._version for p in ns.params])
 
     def refresh_weights(self):
-        """Force re-packing on the next forward (needed only after `param.data = ...` style rebinding)."""
-        self._synced.clear()
+        """Force re-packing on the next forward (needed only after `param.data = ...` style rebinding or after replacing a
+        Parameter object)."""
+        self._native.synced.clear()
+        self._native.params = None
 
     def _apply(self, fn, *args, **kwargs):      # .to() / .cuda() / .float() ... move storage: re-pack
-        self._synced.clear()
+        self._native.synced.clear()
+        self._native.params = None
         return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self._native.params = None
+        return super().load_state_dict(*args, **kwargs)
 
     def _sync_weights(self, h, device: torch.device, stream: int):
         idx = device.index if device.index is not None else torch.cuda.current_device()
         key = self._weights_key()
-        if self._synced.get(idx) == key:
+        if self._native.synced.get(idx) == key:
             return
         lib = _capi.load()
         keep = []
@@ -339,19 +385,51 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
                 keep.append(t)
             _capi.check(lib.hitsir_set_param(h, name.encode(), ctypes.c_void_p(t.data_ptr()), t.numel(), ctypes.c_void_p(stream)))
         _capi.check(lib.hitsir_finalize_weights(h, ctypes.c_void_p(stream)))
-        self._synced[idx] = key
+        self._native.synced[idx] = key
         del keep
 
     def _workspace(self, h, device, B, H, W) -> torch.Tensor:
         key = (device.index, B, H, W)
-        ws = self._workspaces.get(key)
+        ws = self._native.workspaces.get(key)
         if ws is None:
-            n = ctypes.c_size_t()
-            _capi.check(_capi.load().hitsir_workspace_bytes(h, B, H, W, ctypes.byref(n)))
-            self._workspaces.clear()            # one live workspace per module: shapes rarely alternate
-            ws = torch.empty(n.value + 256, dtype=torch.uint8, device=device)
-            self._workspaces[key] = ws
+            self._native.workspaces.clear()     # one live workspace per module: shapes rarely alternate
+            ws = self.new_workspace(device, B, H, W)
+            self._native.workspaces[key] = ws
         return ws
+
+    def new_workspace(self, device, B, H, W) -> torch.Tensor:
+        """A scratch buffer for a (B,H,W) forward that the caller owns (GraphedForward keeps one per captured graph, so that
+        neither a forward with another shape nor a weight update can free memory a captured launch still points to)."""
+        device = torch.device(device)
+        n = ctypes.c_size_t()
+        with torch.cuda.device(device):
+            _capi.check(_capi.load().hitsir_workspace_bytes(self._handle(device), B, H, W, ctypes.byref(n)))
+        return torch.empty(n.value + 256, dtype=torch.uint8, device=device)
+
+    def set_inject(self, device, name: Optional[str], src: Optional[torch.Tensor] = None):
+        """Test hook (stands in for a forward pre-hook that replaces a sub-module's input), see hitsir_set_inject.  `src` is kept
+        alive by the module until cleared."""
+        h = self._handle(torch.device(device))
+        if name is None:
+            self._inject_src = None
+            _capi.check(_capi.load().hitsir_set_inject(h, None, None, 0))
+        else:
+            src = src.detach().to(device=device, dtype=torch.float32).contiguous()
+            self._inject_src = src
+            _capi.check(_capi.load().hitsir_set_inject(h, name.encode(), ctypes.c_void_p(src.data_ptr()), src.numel()))
+
+    def bias_table(self, device, layer: int, block: int) -> torch.Tensor:
+        """The pooled relative-position bias (6, L, Lb) of block (layer, block) as the library precomputed it (hit_sir_pro.py:477-503)."""
+        device = torch.device(device)
+        win = int(self.base_win_size[0] * self.hier_win_ratios[block])
+        base = min(win, self.base_win_size[0])
+        out = torch.empty((6, win * win, base * base), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            h = self._handle(device)
+            self._sync_weights(h, device, stream)
+            _capi.check(_capi.load().hitsir_get_bias_table(h, layer, block, ctypes.c_void_p(out.data_ptr()), out.numel(), ctypes.c_void_p(stream)))
+        return out
 
     def set_tap(self, device, name: Optional[str], dst: Optional[torch.Tensor] = None, stop: bool = True):
         """Test hook (stands in for forward hooks on reference sub-modules), see hitsir_set_tap."""
@@ -403,7 +481,7 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
         with torch.cuda.device(device):
             h = self._handle(device)
             self._sync_weights(h, device, stream)
-            ws = self._workspace(h, device, B, H, W)
+            ws = self._forced_workspace if self._forced_workspace is not None else self._workspace(h, device, B, H, W)
             base = (ws.data_ptr() + 255) // 256 * 256
             y = torch.empty((B, self.in_chans, H * self.upscale, W * self.upscale), dtype=torch.float32, device=device)
             _capi.check(lib.hitsir_forward(h, ctypes.c_void_p(xin.data_ptr()), ctypes.c_void_p(y.data_ptr()), B, H, W,
@@ -473,11 +551,9 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
         self.load_state_dict(sd, strict=True)
         return ck.get("start_epoch") if isinstance(ck, dict) and "start_epoch" in ck else None
 
-    def __del__(self):
-        try:
-            lib = _capi.load()
-            for h in self._handles.values():
-                lib.hitsir_destroy(h)
-            self._handles.clear()
-        except Exception:
-            pass
+    def native_handle(self, device) -> int:
+        """Address of the C handle bound to `device` (None before the first forward there): GraphedForward uses it to notice that the
+        handle a captured graph points into has been replaced."""
+        idx = torch.device(device).index
+        h = self._native.handles.get(idx if idx is not None else torch.cuda.current_device())
+        return None if h is None else h.value

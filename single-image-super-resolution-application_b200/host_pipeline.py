@@ -34,7 +34,12 @@ class HostPipeline:
             slot["done"].synchronize()                     # the slot's previous result has reached the host
         compute = torch.cuda.current_stream(self.device)
         if slot["dx"] is None or slot["dx"].shape != x_host.shape:
-            slot["dx"] = torch.empty(x_host.shape, dtype=torch.float32, device=self.device)
+            # the block may come back from the caching allocator with work of its previous user still queued on the compute stream
+            # (the allocator only orders reuse on the allocating stream): allocate on the copy stream and make it wait for compute
+            self.h2d.wait_stream(compute)
+            with torch.cuda.stream(self.h2d):
+                slot["dx"] = torch.empty(x_host.shape, dtype=torch.float32, device=self.device)
+            slot["dx"].record_stream(compute)
         ev_in, ev_out, ev_done = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
         with torch.cuda.stream(self.h2d):
             slot["dx"].copy_(x_host, non_blocking=True)

@@ -36,3 +36,18 @@ def mse_y(sr: torch.Tensor, hr: torch.Tensor, clip: bool = True) -> torch.Tensor
 def psnr_y(sr: torch.Tensor, hr: torch.Tensor, clip: bool = True) -> torch.Tensor:
     """Per-image Y-channel PSNR in dB (data_range = 1), float64 CUDA tensor of shape (B,); +inf for identical images like skimage."""
     return 10.0 * torch.log10(1.0 / mse_y(sr, hr, clip))
+
+
+def to_uint8_hwc(y: torch.Tensor) -> torch.Tensor:
+    """`to_pil_image(y.clip(0, 1))` of test_experiment.py:75-77 on the device: fp32 (B,C,H,W) -> uint8 (B,H,W,C), value * 255 truncated
+    (C ABI `hitsir_f32nchw_to_u8hwc`).  The multi-GPU output gather moves this form: a quarter of the fp32 bytes."""
+    if y.device.type != "cuda" or y.dim() != 4:
+        raise RuntimeError("to_uint8_hwc expects a (B,C,H,W) CUDA tensor: there is no CPU path.")
+    y = y.contiguous().float()
+    B, C, H, W = y.shape
+    out = torch.empty((B, H, W, C), dtype=torch.uint8, device=y.device)
+    with torch.cuda.device(y.device):
+        stream = torch.cuda.current_stream(y.device).cuda_stream
+        _capi.check(_capi.load().hitsir_f32nchw_to_u8hwc(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(out.data_ptr()), B, C, H, W,
+                                                          ctypes.c_void_p(stream)))
+    return out

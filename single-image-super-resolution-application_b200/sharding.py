@@ -116,9 +116,13 @@ class ShardedSR:
         local = torch.zeros((per, b, c, th * s, tw * s), dtype=torch.float32, device=x.device)
         for k, o in enumerate(outs):
             local[k] = o
-        if world > 1:
+        if world > 1 and dst_rank is None:
             buf = torch.empty((world * per, b, c, th * s, tw * s), dtype=torch.float32, device=x.device)
             dist.all_gather_into_tensor(buf, local, group=self.group)
+        elif world > 1:
+            # only `dst_rank` stitches: a GATHER moves 1/world of what an all-gather would put on every link
+            buf = torch.empty((world * per, b, c, th * s, tw * s), dtype=torch.float32, device=x.device) if rank == dst_rank else None
+            dist.gather(local, list(buf.split(per)) if rank == dst_rank else None, dst=dst_rank, group=self.group)
         else:
             buf = local
         if dst_rank is not None and rank != dst_rank:
@@ -128,7 +132,10 @@ class ShardedSR:
 
 
 class PeerGather:
-    """All-gather of equal per-rank slices by peer-to-peer copies over NVLink instead of an NCCL kernel.
+    """Gather / all-gather of equal per-rank slices by peer-to-peer copies over NVLink instead of an NCCL kernel.
+
+    mode="allgather": every rank ends up with every slice.  mode="gather": only rank `dst` does -- each rank writes its slice into row
+    `rank` of dst's buffer and nothing else moves, 1/world of the all-gather's traffic per GPU (what "reassemble the outputs" needs).
 
     Every rank owns `slots` symmetric output buffers [world, *slice] (torch symmetric memory: the same allocation is mapped into every
     peer's address space).  `start(y, slot)` enqueues, on a side stream, a device-side barrier (all ranks have released the slot), one
@@ -138,7 +145,9 @@ class PeerGather:
     for SMs -- which is what keeps 8-GPU weak scaling at the 1-GPU step time.  NVLink/NVSwitch only (same node); construct it
     collectively on every rank of the group."""
 
-    def __init__(self, slice_shape, dtype, device, group=None, slots: int = 2):
+    def __init__(self, slice_shape, dtype, device, group=None, slots: int = 2, mode: str = "allgather", dst: int = 0):
+        assert mode in ("allgather", "gather")
+        self.mode, self.dst = mode, dst
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group if group is not None else dist.group.WORLD
         name = self.group.group_name
@@ -168,14 +177,17 @@ class PeerGather:
         self.stream.wait_stream(torch.cuda.current_stream(self.device))      # y_local is ready; this rank no longer reads the slot
         with torch.cuda.stream(self.stream):
             self.hdls[slot].barrier(channel=0)
-            for k in range(self.world):                                       # start with the neighbour: spreads the load over the switch
-                p = (self.rank + k) % self.world
-                self.peers[slot][p][self.rank].copy_(y_local, non_blocking=True)
+            if self.mode == "gather":
+                self.peers[slot][self.dst][self.rank].copy_(y_local, non_blocking=True)
+            else:
+                for k in range(self.world):                                   # start with the neighbour: spreads the load over the switch
+                    p = (self.rank + k) % self.world
+                    self.peers[slot][p][self.rank].copy_(y_local, non_blocking=True)
             self.hdls[slot].barrier(channel=1)
         y_local.record_stream(self.stream)
 
     def wait(self, slot: int) -> torch.Tensor:
         """Makes the current stream wait for the gather started on `slot`; returns the [world, *slice] buffer (valid until the slot's
-        next `start`)."""
+        next `start`; in "gather" mode only rank `dst` holds the data)."""
         torch.cuda.current_stream(self.device).wait_stream(self.stream)
         return self.bufs[slot]

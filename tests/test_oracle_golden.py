@@ -42,6 +42,77 @@ def test_oracle_matches_reference_golden(name):
     assert checked >= 15
 
 
+def test_oracle_matches_reference_scc_parts():
+    """SCC.forward piece by piece: pooled relative-position bias (6, L, Lb) of hit_sir_pro.py:477-503, S-SC (:458-513)
+    and C-SC (:515-540) for all six window sizes, against values recorded from the unmodified reference (make_golden_r2.py scc)."""
+    g, meta = load_golden("scc_parts_56x72")
+    model, oracle = build_pair(meta["flags"], meta["upsampler"], meta["upscale"], meta["mode"], meta["wseed"])
+    x = synthetic_image(*meta["shape"], seed=meta["xseed"])
+    taps = {}
+    with torch.no_grad():
+        oracle.forward(x, taps)
+    for j in range(6):
+        scc = taps[f"block0.{j}.scc"]                       # (B,H,W,180) = [S-SC 90 | C-SC 90] (:596)
+        for kind, part in (("ssc", scc[..., :90]), ("csc", scc[..., 90:])):
+            ref = torch.from_numpy(g[f"{kind}{j}"])
+            got = part.reshape(-1)[::meta["s_stride"]]
+            assert got.shape == ref.shape
+            assert (got - ref).abs().max().item() <= 2e-5 * (ref.abs().max().item() + 1e-6), (kind, j)
+        bias = oracle.pooled_bias(0, j)
+        assert list(bias.shape) == list(g[f"bias{j}_shape"])
+        ref = torch.from_numpy(g[f"bias{j}"])
+        assert (bias.reshape(-1)[::meta["b_stride"]] - ref).abs().max().item() < 2e-6, j
+
+
+def test_oracle_matches_reference_single_channel():
+    """in_chans = 1: no RGB mean (hit_sir_pro.py:1130-1131), one-channel conv_first / upsample head."""
+    g, meta = load_golden("gray_x4_direct_40x44")
+    model, oracle = build_pair(meta["flags"], meta["upsampler"], meta["upscale"], meta["mode"], meta["wseed"], in_chans=1)
+    assert "\n".join(f"{k} {tuple(v.shape)}" for k, v in model.state_dict().items()) == str(g["keys"])
+    x = synthetic_image(*meta["shape"], seed=meta["xseed"], chans=1)
+    with torch.no_grad():
+        y = oracle(x)
+    ref = torch.from_numpy(g["y"])
+    assert y.shape == ref.shape == (2, 1, 160, 176)
+    assert (y - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+BIG_CASES = ["big_cfg3_tile576_x2ps_init", "big_cfg3_tile576_x2ps_stress", "big_cfg4_512_x4_init", "big_cfg4_512_x4_stress"]
+
+
+def check_big(y, g, tol_abs, min_psnr=None):
+    """Compare a full-size output with the strided sample / crops / moments kept in a big_* fixture.  Returns (max-abs, psnr) over the
+    compared values, normalised like tests.helpers.assert_close."""
+    from tests.helpers import psnr
+    scale = max(1.0, float(g["absmax"]))
+    got = [y.reshape(-1)[::int(g["stride"])]]
+    ref = [torch.from_numpy(g["sample"])]
+    c = int(g["crop"])
+    for i, (y0, x0) in enumerate(g["origins"]):
+        got.append(y[0, :, y0:y0 + c, x0:x0 + c].reshape(-1))
+        ref.append(torch.from_numpy(g[f"crop{i}"]).reshape(-1))
+    got, ref = torch.cat(got), torch.cat(ref)
+    assert got.shape == ref.shape and torch.isfinite(got).all()
+    err = (got - ref).abs().max().item() / scale
+    p = psnr(got / scale, ref / scale)
+    assert err < tol_abs, (err, scale)
+    if min_psnr is not None:
+        assert p > min_psnr, p
+    assert abs(y.double().mean().item() - float(g["mean"])) < tol_abs * scale
+    return err, p
+
+
+@pytest.mark.skipif(os.environ.get("HITSIR_SLOW_TESTS") != "1", reason="minutes of CPU per case: HITSIR_SLOW_TESTS=1 to run")
+@pytest.mark.parametrize("name", BIG_CASES)
+def test_oracle_matches_reference_at_baseline_sizes(name):
+    g, meta = load_golden(name)
+    model, oracle = build_pair(meta["flags"], meta["upsampler"], meta["upscale"], meta["mode"], meta["wseed"])
+    x = synthetic_image(*meta["shape"], seed=meta["xseed"])
+    with torch.no_grad():
+        y = oracle(x)
+    check_big(y, g, 5e-5)
+
+
 def test_known_answer_param_count():
     # logs/.../模型参数量.txt:1 of the reference: the one known-answer value that pins the architecture
     m = hitsir_b200.HiT_SIR(True, True, True, **hitsir_b200.PRO_KWARGS)
