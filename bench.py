@@ -294,11 +294,11 @@ def run_cfg3(hitsir_b200, dev, world, rank):
     g.manual_seed(99)
     frame = torch.rand(1, 3, 1080, 1920, device=dev, generator=g)
     sharded = ShardedSR(model, scale)
-    origins = tile_plan(1080, 1920, 576, 576 - 448)            # x origins 0,448,896,1344; y origins 0,504
+    origins = tile_plan(1080, 1920, 576, 72)                   # KAIR stride 504: x origins 0,504,1008,1344; y origins 0,504 -> 8 tiles
     out = {}
 
     def step():
-        out["y"] = sharded.forward_tiled(frame, tile=576, overlap=576 - 448, dst_rank=0)
+        out["y"] = sharded.forward_tiled(frame, tile=576, overlap=72, dst_rank=0)
     with torch.no_grad():
         for _ in range(2):
             step()

@@ -162,8 +162,40 @@ def make_scc():
     print(f"{name} -> {os.path.getsize(path) / 1e3:.0f} kB", flush=True)
 
 
+def make_yardstick():
+    """The reference's OWN bf16 error: the unmodified module under torch.autocast(bfloat16) against its fp32 run, for every golden case.
+    north_star allows "bf16/fp32 compute" within a stated tolerance; this is the yardstick that tolerance is stated against
+    (tests/helpers.py: the CUDA path may be at most 1.5x as far from the fp32 reference as the reference's own autocast run)."""
+    import json
+    import math
+    sys.path.insert(0, HERE)
+    from make_golden import CASES as SMALL
+    cases = [(n, f, u, s, m, ws, sh, xs, 3) for (n, f, u, s, m, ws, sh, xs) in SMALL]
+    cases += [(n, f, u, s, m, ws, sh, xs, 3) for (n, f, u, s, m, ws, sh, xs, _st, _c) in BIG]
+    cases.append(("gray_x4_direct_40x44", (False, True, True), "pixelshuffledirect", 4, "stress", 15, (2, 40, 44), 25, 1))
+    path = os.path.join(HERE, "bf16_yardstick.json")
+    out = json.load(open(path)) if os.path.exists(path) else {}
+    for name, flags, up, scale, mode, wseed, shape, xseed, ic in cases:
+        if name in out:
+            continue
+        m, _ = build(flags, up, scale, mode, wseed, in_chans=ic)
+        x = synthetic_image(*shape, seed=xseed, chans=ic)
+        with torch.no_grad():
+            y = m(x)
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                yb = m(x).float()
+        scale_ = max(1.0, y.abs().max().item())
+        err = (y - yb).abs().max().item() / scale_
+        mse = (((y - yb) / scale_).double() ** 2).mean().item()
+        out[name] = {"max_abs": err, "psnr": 10.0 * math.log10(1.0 / mse), "mode": mode, "shape": list(shape)}
+        print(name, out[name], flush=True)
+        json.dump(out, open(path, "w"), indent=1)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["small", "scc", "big"]
+    if "yardstick" in what:
+        make_yardstick()
     if "small" in what:
         make_small()
     if "scc" in what:
