@@ -71,6 +71,8 @@ typedef struct HitsirConfig {
   int32_t upsampler;                      /* HITSIR_UP_* */
   int32_t num_ratios;
   float hier_win_ratios[HITSIR_MAX_DEPTH];
+  int32_t resi_3conv;                     /* resi_connection: 0 = '1conv', 1 = '3conv' (:913-918, :1224-1231) */
+  int32_t ape_tokens;                     /* ape=True: (img_size / patch_size)^2 rows of absolute_pos_embed (:1187-1189); 0 = off */
 } HitsirConfig;
 
 typedef struct HitsirHandle HitsirHandle;

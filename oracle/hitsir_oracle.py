@@ -224,6 +224,16 @@ def conv_ffn(x: Tensor, sd, p: str) -> Tensor:
     return F.linear(h, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
 
 
+def resi_conv(t: Tensor, sd, p: str) -> Tensor:
+    """The conv before a residual connection: '1conv' = Conv2d(C, C, 3) (:911-912, :1221-1222); '3conv' = Conv3x3(C -> C/4), LeakyReLU(0.2),
+    Conv1x1, LeakyReLU(0.2), Conv3x3(C/4 -> C) (:913-918, :1224-1231).  Told apart by the state_dict keys.  NHWC in/out."""
+    if p + "weight" in sd:
+        return conv_nhwc(t, sd[p + "weight"], sd[p + "bias"], 1)
+    t = F.leaky_relu(conv_nhwc(t, sd[p + "0.weight"], sd[p + "0.bias"], 1), 0.2)
+    t = F.leaky_relu(conv_nhwc(t, sd[p + "2.weight"], sd[p + "2.bias"], 0), 0.2)
+    return conv_nhwc(t, sd[p + "4.weight"], sd[p + "4.bias"], 1)
+
+
 def ln(x: Tensor, sd, p: str) -> Tensor:
     return F.layer_norm(x, (x.shape[-1],), sd[p + "weight"], sd[p + "bias"], 1e-5)
 
@@ -312,6 +322,8 @@ class HiTSIROracle:
             taps["shallow"] = shallow
         # forward_features (:1284-1302); patch_embed = flatten + LayerNorm (:975-983)
         t = ln(shallow, sd, "patch_embed.norm.")
+        if "absolute_pos_embed" in sd:                 # ape=True (:1293-1294): (1, num_patches, C) broadcast over the batch; H*W must equal num_patches
+            t = t + sd["absolute_pos_embed"].view(1, H, W, -1)
         if taps is not None:
             taps["embed"] = t
         for i in range(len(cfg.depths)):
@@ -319,13 +331,13 @@ class HiTSIROracle:
             for j in range(cfg.depths[i]):
                 t = self.block(t, i, j, taps)
             # RHTB.forward (:928-936)
-            t = conv_nhwc(t, sd[f"layers.{i}.conv.weight"], sd[f"layers.{i}.conv.bias"], 1) + t_in
+            t = resi_conv(t, sd, f"layers.{i}.conv.") + t_in
             if taps is not None:
                 taps[f"layer{i}"] = t
         t = ln(t, sd, "norm.")
         if taps is not None:
             taps["norm"] = t
-        cab = conv_nhwc(t, sd["conv_after_body.weight"], sd["conv_after_body.bias"], 1)
+        cab = resi_conv(t, sd, "conv_after_body.")
         if taps is not None:
             taps["conv_after_body"] = cab
         if cfg.is_fusion:
@@ -364,6 +376,6 @@ class HiTSIROracle:
         else:                                      # :1335-1340 (denoise mode)
             y = x + F.conv2d(fn, sd["conv_last.weight"], sd["conv_last.bias"], 1, 1)
         y = y / cfg.img_range + mean
-        return y[:, :, :H * cfg.upscale, :W * cfg.upscale]
+        return y[:, :, :H * cfg.upscale, :W * cfg.upscale]     # upsampler=None: y is x-sized and the slice is a no-op (:1344)
 
     __call__ = forward

@@ -36,6 +36,8 @@ class HitsirConfig(C.Structure):
         ("upsampler", C.c_int32),
         ("num_ratios", C.c_int32),
         ("hier_win_ratios", C.c_float * HITSIR_MAX_DEPTH),
+        ("resi_3conv", C.c_int32),
+        ("ape_tokens", C.c_int32),
     ]
 
 

@@ -118,6 +118,8 @@ struct HitsirHandle {
   std::vector<std::vector<BlockW>> blocks;
   std::vector<GemmW> layer_conv;
   GemmW conv_after_body;
+  // resi_connection='3conv': [C -> C/4 3x3] LeakyReLU [C/4 -> C/4 1x1] LeakyReLU [C/4 -> C 3x3]; index num_layers = conv_after_body
+  std::vector<GemmW> r3_a, r3_b, r3_c;
   UaPack ua[3];
   GemmW conv_before_upsample, conv_up1, conv_up2, conv_hr, conv_last;
   std::vector<GemmW> upsample;   // pixelshuffle stages / pixelshuffledirect
@@ -169,6 +171,7 @@ void build_param_list(HitsirHandle* h) {
       add_wb(h, p + ".conv_last", (int64_t)C * C * 9, C);
     }
   }
+  if (c.ape_tokens > 0) add_param(h, "absolute_pos_embed", (int64_t)c.ape_tokens * C);
   add_wb(h, "patch_embed.norm", C, C);
   const int hd = C / (2 * c.num_heads[0]);
   const int pos_dim = (C / 4) / 4;
@@ -202,10 +205,23 @@ void build_param_list(HitsirHandle* h) {
       add_wb(h, p + ".mlp.dwconv.depthwise_conv.0", (int64_t)hidden * 25, hidden);
       add_wb(h, p + ".mlp.fc2", (int64_t)C * hidden, C);
     }
-    add_wb(h, "layers." + std::to_string(i) + ".conv", (int64_t)C * C * 9, C);
+    if (c.resi_3conv) {
+      const std::string p = "layers." + std::to_string(i) + ".conv";
+      add_wb(h, p + ".0", (int64_t)(C / 4) * C * 9, C / 4);
+      add_wb(h, p + ".2", (int64_t)(C / 4) * (C / 4), C / 4);
+      add_wb(h, p + ".4", (int64_t)C * (C / 4) * 9, C);
+    } else {
+      add_wb(h, "layers." + std::to_string(i) + ".conv", (int64_t)C * C * 9, C);
+    }
   }
   add_wb(h, "norm", C, C);
-  add_wb(h, "conv_after_body", (int64_t)C * C * 9, C);
+  if (c.resi_3conv) {
+    add_wb(h, "conv_after_body.0", (int64_t)(C / 4) * C * 9, C / 4);
+    add_wb(h, "conv_after_body.2", (int64_t)(C / 4) * (C / 4), C / 4);
+    add_wb(h, "conv_after_body.4", (int64_t)C * (C / 4) * 9, C);
+  } else {
+    add_wb(h, "conv_after_body", (int64_t)C * C * 9, C);
+  }
   const int s = c.upscale;
   switch (c.upsampler) {
     case HITSIR_UP_PIXELSHUFFLE:
@@ -268,7 +284,7 @@ int validate_config(const HitsirConfig& c) {
   if (c.upsampler == HITSIR_UP_PIXELSHUFFLEDIRECT && (c.upscale < 1 || c.upscale * c.upscale * c.in_chans > 256)) {
     set_error("pixelshuffledirect upscale %d not supported", c.upscale); return HITSIR_ERR_UNSUPPORTED;
   }
-  if (c.upsampler == HITSIR_UP_NONE && c.upscale != 1) { set_error("upsampler=None requires upscale == 1 (x + conv_last(res), hit_sir_pro.py:1340)"); return HITSIR_ERR_INVALID; }
+  if (c.ape_tokens < 0) { set_error("ape_tokens must be >= 0"); return HITSIR_ERR_INVALID; }
   return 0;
 }
 
@@ -415,9 +431,17 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
       if (dev_alloc(h, &bw.w2_img, (size_t)6 * 192 * 128)) return 1;
       if (launch_pack_w2_image(bw.fc2.w, bw.w2_img, st)) return 1;
     }
-    if (make_gemm_w(h, &h->layer_conv[i], "layers." + std::to_string(i) + ".conv", C, C, 9, st)) return 1;
+    if (!c.resi_3conv && make_gemm_w(h, &h->layer_conv[i], "layers." + std::to_string(i) + ".conv", C, C, 9, st)) return 1;
   }
-  if (make_gemm_w(h, &h->conv_after_body, "conv_after_body", C, C, 9, st)) return 1;
+  if (c.resi_3conv) {
+    h->r3_a.assign(c.num_layers + 1, GemmW()); h->r3_b.assign(c.num_layers + 1, GemmW()); h->r3_c.assign(c.num_layers + 1, GemmW());
+    for (int i = 0; i <= c.num_layers; ++i) {
+      const std::string p = i < c.num_layers ? "layers." + std::to_string(i) + ".conv" : std::string("conv_after_body");
+      if (make_gemm_w(h, &h->r3_a[i], p + ".0", C / 4, C, 9, st)) return 1;
+      if (make_gemm_w(h, &h->r3_b[i], p + ".2", C / 4, C / 4, 1, st)) return 1;
+      if (make_gemm_w(h, &h->r3_c[i], p + ".4", C, C / 4, 9, st)) return 1;
+    }
+  } else if (make_gemm_w(h, &h->conv_after_body, "conv_after_body", C, C, 9, st)) return 1;
   if (c.is_fusion) {
     for (int u = 0; u < 3; ++u) {
       const std::string p = "fusion.union_attention" + std::to_string(u + 1);
@@ -787,6 +811,26 @@ int union_attention(Fwd& f, int u, const float* a, const float* b, float* out) {
   return conv3(f, "conv_ua", h->ua[u].conv_last, ws.outsc, f.B, f.H, f.W, kCp, p);
 }
 
+// resi_connection='3conv' (:913-918, :1224-1231): out = conv3x3(C/4 -> C)(lrelu(conv1x1(lrelu(conv3x3(C -> C/4)(in))))) (+ res).
+// The two C/4 = 45-channel maps live as bf16 [N, 64] in the (idle) self-correlation output buffer.
+int resi_3conv(Fwd& f, int idx, const char* cat, const bf16* in, const float* res, float* out) {
+  HitsirHandle* h = f.h;
+  Workspace& ws = f.ws;
+  const int C4 = kC / 4;
+  bf16* t1 = ws.outsc;
+  bf16* t2 = ws.outsc + f.N * 64;
+  GemmParams p;
+  base_params(p, h->r3_a[idx]);
+  p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = C4; p.out_bf16 = t1; p.ldb = 64;
+  RUN(conv3(f, cat, h->r3_a[idx], in, f.B, f.H, f.W, kCp, p));
+  base_params(p, h->r3_b[idx]);
+  p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = C4; p.out_bf16 = t2; p.ldb = 64;
+  RUN(linear(f, cat, h->r3_b[idx], t1, f.N, p));
+  base_params(p, h->r3_c[idx]);
+  p.epi = EPI_STORE; p.n_real = kC; p.res = res; p.ldr = kC; p.out_f32 = out; p.ldf = kC;
+  return conv3(f, cat, h->r3_c[idx], t2, f.B, f.H, f.W, 64, p);
+}
+
 int forward_impl(Fwd& f, const float* x, float* y) {
   HitsirHandle* h = f.h;
   const HitsirConfig& c = h->cfg;
@@ -813,7 +857,12 @@ int forward_impl(Fwd& f, const float* x, float* y) {
     RUN(linear(f, "gemm_first", h->first, A0, N, p));
   }
   // patch_embed LayerNorm (:975-983): shallow features S stay for the fusion, the stream starts from LN(S)
-  LAUNCH("ln_rows", 1, launch_ln_rows(ws.S, pe_g, pe_b, nullptr, ws.P, N, f.st));
+  if (c.ape_tokens > 0 && (long long)H * W != c.ape_tokens) {
+    // x + absolute_pos_embed broadcasts (1, num_patches, C) against (B, H*W, C): any other size raises in the reference (:1294)
+    set_error("The size of tensor a (%lld) must match the size of tensor b (%d) at non-singleton dimension 1 (absolute_pos_embed)", (long long)H * W, c.ape_tokens);
+    return HITSIR_ERR_INVALID;
+  }
+  LAUNCH("ln_rows", 1, launch_ln_rows(ws.S, pe_g, pe_b, nullptr, ws.P, N, f.st, c.ape_tokens > 0 ? P(h, "absolute_pos_embed") : nullptr, c.ape_tokens));
   TAP("shallow", ws.S, 0, kC, N, kC);
   TAP("embed", ws.P, 0, kC, N, kC);
   // ---- deep features: RHTB stack (:1296-1297, :928-936)
@@ -822,18 +871,26 @@ int forward_impl(Fwd& f, const float* x, float* y) {
       RUN(forward_block(f, i, j, j == 0 ? ws.P : ws.Q, ws.Q));
       if (f.stopped) return 0;
     }
-    base_params(p, h->layer_conv[i]);
-    p.epi = EPI_STORE; p.n_real = kC; p.res = ws.P; p.ldr = kC; p.out_f32 = ws.P; p.ldf = kC;
-    RUN(conv3(f, "conv_layer", h->layer_conv[i], ws.xb0, B, H, W, kCp, p));
+    if (c.resi_3conv) {
+      RUN(resi_3conv(f, i, "conv_layer", ws.xb0, ws.P, ws.P));
+    } else {
+      base_params(p, h->layer_conv[i]);
+      p.epi = EPI_STORE; p.n_real = kC; p.res = ws.P; p.ldr = kC; p.out_f32 = ws.P; p.ldf = kC;
+      RUN(conv3(f, "conv_layer", h->layer_conv[i], ws.xb0, B, H, W, kCp, p));
+    }
     TAP(("layer" + std::to_string(i)).c_str(), ws.P, 0, kC, N, kC);
   }
   // ---- final norm + conv_after_body (:1299-1300, :1317/1324/1330/1339)
   LAUNCH("ln_rows", 1, launch_ln_rows(ws.P, P(h, "norm.weight"), P(h, "norm.bias"), ws.xb0, nullptr, N, f.st));
   TAP("norm", ws.xb0, 1, kCp, N, kC);
   float* CAB = ws.Q;
-  base_params(p, h->conv_after_body);
-  p.epi = EPI_STORE; p.n_real = kC; p.out_f32 = CAB; p.ldf = kC;
-  RUN(conv3(f, "conv_after_body", h->conv_after_body, ws.xb0, B, H, W, kCp, p));
+  if (c.resi_3conv) {
+    RUN(resi_3conv(f, c.num_layers, "conv_after_body", ws.xb0, nullptr, CAB));
+  } else {
+    base_params(p, h->conv_after_body);
+    p.epi = EPI_STORE; p.n_real = kC; p.out_f32 = CAB; p.ldf = kC;
+    RUN(conv3(f, "conv_after_body", h->conv_after_body, ws.xb0, B, H, W, kCp, p));
+  }
   TAP("conv_after_body", CAB, 0, kC, N, kC);
   // ---- fusion(conv_after_body(deep), shallow): positional binding (:1330 -> :145)
   bf16* F = ws.xb1;
@@ -920,8 +977,10 @@ int forward_impl(Fwd& f, const float* x, float* y) {
     last_params(p, h->upsample[0], s);
     RUN(conv3(f, "conv_last_direct", h->upsample[0], F, B, H, W, kCp, p));
   } else {
-    set_error("upsampler=None (x + conv_last(res)) is not implemented in this build");
-    return HITSIR_ERR_UNSUPPORTED;
+    // upsampler=None / '' (:1335-1342): y = (x_shifted + conv_last(res)) / img_range + mean = x + conv_last(res) / img_range, same size as x
+    last_params(p, h->conv_last, 1);
+    p.res_img = x;
+    RUN(conv3(f, "conv_last_none", h->conv_last, F, B, H, W, kCp, p));
   }
   return 0;
 }
@@ -1043,7 +1102,8 @@ HITSIR_API int hitsir_forward_host(HitsirHandle* h, const float* host_x, float* 
                         void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || !host_x || !host_y || !dev_x || !dev_y) { set_error("hitsir_forward_host: null argument"); return HITSIR_ERR_INVALID; }
   const size_t in_b = (size_t)B * h->cfg.in_chans * H * W * sizeof(float);
-  const size_t out_b = in_b * h->cfg.upscale * h->cfg.upscale;
+  const int se = h->cfg.upsampler == HITSIR_UP_NONE ? 1 : h->cfg.upscale;       // upsampler=None returns x-sized images whatever `upscale` says (:1344)
+  const size_t out_b = in_b * se * se;
   HITSIR_CHECK(cudaMemcpyAsync(dev_x, host_x, in_b, cudaMemcpyHostToDevice, (cudaStream_t)stream));
   int rc = hitsir_forward(h, dev_x, dev_y, B, H, W, workspace, workspace_bytes, stream);
   if (rc) return rc;
@@ -1054,7 +1114,7 @@ HITSIR_API int hitsir_forward_host(HitsirHandle* h, const float* host_x, float* 
 HITSIR_API int hitsir_forward_u8(HitsirHandle* h, const uint8_t* x_hwc, uint8_t* y_hwc, int B, int H, int W, float* dev_x, float* dev_y,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   if (!h || !x_hwc || !y_hwc || !dev_x || !dev_y) { set_error("hitsir_forward_u8: null argument"); return HITSIR_ERR_INVALID; }
-  const int s = h->cfg.upscale, ic = h->cfg.in_chans;
+  const int s = h->cfg.upsampler == HITSIR_UP_NONE ? 1 : h->cfg.upscale, ic = h->cfg.in_chans;
   if (launch_u8hwc_to_f32nchw(x_hwc, dev_x, B, H, W, ic, (cudaStream_t)stream)) return HITSIR_ERR_CUDA;
   int rc = hitsir_forward(h, dev_x, dev_y, B, H, W, workspace, workspace_bytes, stream);
   if (rc) return rc;

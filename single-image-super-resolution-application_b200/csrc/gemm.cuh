@@ -45,6 +45,7 @@ struct GemmParams {
   int shuf_c;        // channels after shuffle (NCHW: image channels; BF16: feature channels = ldb)
   float out_scale;   // 1 / img_range
   float mean[4];     // per-channel mean added after scaling (NCHW)
+  const float* res_img;   // EPI_SHUFFLE_NCHW, ps == 1: NCHW fp32 image added INSTEAD of the mean (upsampler=None: x + conv_last(res), :1340-1342)
   // debug / SIMT cross-check operand views
   const bf16* A; int lda;         // linear: [M, lda]; conv: NHWC base with lda = Cin_pad
   const bf16* Wp; int ldw;        // [n_tiles*BN, ldw]
@@ -243,7 +244,8 @@ __device__ __forceinline__ void epilogue_row(const GemmParams& p, Acc& acc, cons
         const int oy = ri.y * ps + rem / ps, ox = ri.x * ps + rem % ps;
         float t = v[i] + __ldg(p.bias + co);
         if (p.epi == EPI_SHUFFLE_NCHW) {
-          p.out_f32[(((long long)ri.b * p.shuf_c + c) * oh + oy) * ow + ox] = t * p.out_scale + p.mean[c & 3];
+          const long long oi = (((long long)ri.b * p.shuf_c + c) * oh + oy) * ow + ox;
+          p.out_f32[oi] = t * p.out_scale + (p.res_img != nullptr ? __ldg(p.res_img + oi) : p.mean[c & 3]);
         } else {
           if (p.act == ACT_LRELU) t = lrelu(t, p.slope);
           p.out_bf16[(((long long)ri.b * oh + oy) * ow + ox) * p.ldb + c] = __float2bfloat16(t);

@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(256) entry_im2col_kernel(const float* __restri
 
 // one warp per row
 __global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                               bf16* __restrict__ ob, float* __restrict__ of, long long N) {
+                               bf16* __restrict__ ob, float* __restrict__ of, long long N, const float* __restrict__ add, long long add_rows) {
   const int lane = threadIdx.x & 31;
   const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -84,7 +84,8 @@ __global__ void ln_rows_kernel(const float* __restrict__ x, const float* __restr
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const int c = lane + 32 * i;
-      const float y = c < kC ? (v[i] - mean) * rstd * gamma[c] + beta[c] : 0.f;
+      float y = c < kC ? (v[i] - mean) * rstd * gamma[c] + beta[c] : 0.f;
+      if (add != nullptr && c < kC) y += add[(row % add_rows) * kC + c];       // absolute position embedding, broadcast over the batch (:1293-1294)
       if (ob != nullptr) ob[row * kCp + c] = __float2bfloat16(y);
       if (of != nullptr && c < kC) of[row * kC + c] = y;
     }
@@ -833,8 +834,9 @@ int launch_entry_im2col(const float* x, bf16* a0, int B, int H, int W, int in_ch
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
-int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* ob, float* of, long long N, cudaStream_t st) {
-  ln_rows_kernel<<<grid_for(N * 32, 256), 256, 0, st>>>(x, gamma, beta, ob, of, N);
+int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* ob, float* of, long long N, cudaStream_t st, const float* add,
+                   long long add_rows) {
+  ln_rows_kernel<<<grid_for(N * 32, 256), 256, 0, st>>>(x, gamma, beta, ob, of, N, add, add_rows > 0 ? add_rows : 1);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

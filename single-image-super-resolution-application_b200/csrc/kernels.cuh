@@ -17,7 +17,9 @@ constexpr int kHidp = 384;
 int launch_entry_im2col(const float* x, bf16* a0, int B, int H, int W, int in_ch, int f, int Kp,
                         const float* mean3, float img_range, cudaStream_t st);
 // LayerNorm over rows of fp32 [N,180] -> bf16 [N,192] (pad zero) and/or fp32 [N,180]
-int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* out_bf16, float* out_f32, long long N, cudaStream_t st);
+// add (optional): fp32 [add_rows, 180] added after the normalisation, row index modulo add_rows (absolute position embedding)
+int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* out_bf16, float* out_f32, long long N, cudaStream_t st,
+                   const float* add = nullptr, long long add_rows = 0);
 // depthwise 5x5 (zero pad 2) + bias -> GELU -> + input  (ConvFFN middle, hit_sir_pro.py:42)
 int launch_dwconv5_gelu_add(const bf16* h1, const float* w_tap_major, const float* bias, bf16* h2, int B, int H, int W, int num_sms, cudaStream_t st);
 // ffn_tail.cu: dwconv5 + GELU + input fused with fc2 + LayerNorm + residual (x updated in place); tm_w2 = packed fc2 weights, box {64, 192}

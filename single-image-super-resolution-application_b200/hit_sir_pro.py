@@ -6,9 +6,10 @@ state_dict keys (1650 for the "pro" configuration, no buffers), same `forward(x)
 *hold parameters* under the reference's names; no arithmetic of the forward pass happens in
 PyTorch -- `forward` hands raw device pointers to the C ABI (`include/hitsir_b200.h`).
 
-Not provided: autograd/backward, `ape=True`, `resi_connection='3conv'`,
-`upsampler=None`, dropout/drop-path > 0 in training mode; they raise NotImplementedError where
-they would change the result.
+Constructor variants built: all four upsamplers incl. `upsampler=None` (denoise mode), `resi_connection` '1conv' and
+'3conv', `ape=True`, `in_chans` 1 or 3, the three feature flags.  Not provided: autograd/backward, widths other than
+the pro width (embed_dim=180, 6 heads, mlp_ratio=2), `patch_norm=False`, dropout/drop-path > 0 in training mode; they raise
+NotImplementedError where they would change the result.
 """
 from __future__ import annotations
 
@@ -179,11 +180,19 @@ class BasicLayer(_Holder):                  # hit_sir_pro.py:755-823
             for i in range(depth)])
 
 
+def _resi_conv(dim, resi_connection):        # hit_sir_pro.py:911-918, 1221-1231
+    if resi_connection == '1conv':
+        return nn.Conv2d(dim, dim, 3, 1, 1)
+    return nn.Sequential(nn.Conv2d(dim, dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                         nn.Conv2d(dim // 4, dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                         nn.Conv2d(dim // 4, dim, 3, 1, 1))
+
+
 class RHTB(_Holder):                        # hit_sir_pro.py:848-926
-    def __init__(self, is_channel_spatial_attn, dim, depth, num_heads, base_win_size, mlp_ratio, hier_win_ratios):
+    def __init__(self, is_channel_spatial_attn, dim, depth, num_heads, base_win_size, mlp_ratio, hier_win_ratios, resi_connection='1conv'):
         super().__init__()
         self.residual_group = BasicLayer(is_channel_spatial_attn, dim, depth, num_heads, base_win_size, mlp_ratio, hier_win_ratios)
-        self.conv = nn.Conv2d(dim, dim, 3, 1, 1)
+        self.conv = _resi_conv(dim, resi_connection)
 
 
 class PatchEmbed(_Holder):                  # hit_sir_pro.py:939-973
@@ -245,19 +254,24 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
         # what this build cannot compute is refused up front (nothing silently differs from the reference)
         if norm_layer is not nn.LayerNorm:
             raise NotImplementedError("hitsir_b200: only norm_layer=nn.LayerNorm")
-        if ape:
-            raise NotImplementedError("hitsir_b200: ape=True is not implemented")
         if not patch_norm:
             raise NotImplementedError("hitsir_b200: patch_norm=False is not implemented")
-        if resi_connection != '1conv':
-            raise NotImplementedError("hitsir_b200: resi_connection='3conv' is not implemented")
+        if resi_connection not in ('1conv', '3conv'):
+            raise NotImplementedError(f"hitsir_b200: resi_connection={resi_connection!r} is not implemented")
         if upsampler == 'pixelshuffle' and (upscale & (upscale - 1)) == 0 and upscale > 4:
             raise NotImplementedError(f"hitsir_b200: upsampler='pixelshuffle' with upscale={upscale} is not implemented (1, 2, 3, 4)")
         if embed_dim != 180 or any(h != 6 for h in num_heads) or float(mlp_ratio) != 2.0:
             raise NotImplementedError("hitsir_b200 implements the HiT-SIR-pro width: embed_dim=180, num_heads=6, mlp_ratio=2 "
                                       f"(got embed_dim={embed_dim}, num_heads={num_heads}, mlp_ratio={mlp_ratio})")
-        if upsampler not in ('pixelshuffle', 'pixelshuffledirect', 'nearest+conv'):
+        if upsampler not in ('pixelshuffle', 'pixelshuffledirect', 'nearest+conv', None, ''):
             raise NotImplementedError(f"hitsir_b200: upsampler={upsampler!r} is not implemented")
+        self.resi_connection = resi_connection
+        self.img_size, self.patch_size = img_size, patch_size
+        if ape:                                  # direct parameter of the top module: first key of the state_dict, like the reference (:1187-1189)
+            n = img_size if isinstance(img_size, (tuple, list)) else (img_size, img_size)
+            ps = patch_size if isinstance(patch_size, (tuple, list)) else (patch_size, patch_size)
+            self.absolute_pos_embed = nn.Parameter(torch.zeros(1, (n[0] // ps[0]) * (n[1] // ps[1]), embed_dim))
+            _trunc_normal_(self.absolute_pos_embed, std=.02)
 
         # 1. shallow feature extraction (:1139-1154)
         if is_mult_size_conv_feat_extract:
@@ -268,10 +282,10 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
         # 2. deep feature extraction (:1158-1231)
         self.patch_embed = PatchEmbed(embed_dim, norm_layer if patch_norm else None)
         self.layers = nn.ModuleList([
-            RHTB(is_channel_spatial_attn, embed_dim, depths[i], num_heads[i], base_win_size, mlp_ratio, hier_win_ratios)
+            RHTB(is_channel_spatial_attn, embed_dim, depths[i], num_heads[i], base_win_size, mlp_ratio, hier_win_ratios, resi_connection)
             for i in range(self.num_layers)])
         self.norm = norm_layer(embed_dim)
-        self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+        self.conv_after_body = _resi_conv(embed_dim, resi_connection)
         # 3. reconstruction (:1235-1262)
         if upsampler == 'pixelshuffle':
             self.conv_before_upsample = nn.Sequential(nn.Conv2d(embed_dim, num_feat, 3, 1, 1), nn.LeakyReLU(inplace=True))
@@ -286,6 +300,8 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
             self.conv_up2 = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
             self.conv_hr = nn.Conv2d(num_feat, num_feat, 3, 1, 1)
             self.conv_last = nn.Conv2d(num_feat, in_chans, 3, 1, 1)
+        else:                                    # denoising / compression-artefact mode (:1260-1262): x + conv_last(res)
+            self.conv_last = nn.Conv2d(embed_dim, in_chans, 3, 1, 1)
         self.apply(self._init_weights)
 
         # native state (never part of state_dict, never copied or pickled: see _NativeState)
@@ -327,7 +343,14 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
         c.num_ratios = len(self.hier_win_ratios)
         for i, r in enumerate(self.hier_win_ratios):
             c.hier_win_ratios[i] = float(r)
+        c.resi_3conv = 1 if self.resi_connection == '3conv' else 0
+        c.ape_tokens = int(self.absolute_pos_embed.shape[1]) if self.ape else 0
         return c
+
+    @property
+    def out_scale(self) -> int:
+        """Spatial factor of the output: `upscale`, except upsampler=None, whose forward returns x-sized images (:1340-1344)."""
+        return self.upscale if self.upsampler else 1
 
     def _handle(self, device: torch.device) -> ctypes.c_void_p:
         idx = device.index if device.index is not None else torch.cuda.current_device()
@@ -483,7 +506,7 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
             self._sync_weights(h, device, stream)
             ws = self._forced_workspace if self._forced_workspace is not None else self._workspace(h, device, B, H, W)
             base = (ws.data_ptr() + 255) // 256 * 256
-            y = torch.empty((B, self.in_chans, H * self.upscale, W * self.upscale), dtype=torch.float32, device=device)
+            y = torch.empty((B, self.in_chans, H * self.out_scale, W * self.out_scale), dtype=torch.float32, device=device)
             _capi.check(lib.hitsir_forward(h, ctypes.c_void_p(xin.data_ptr()), ctypes.c_void_p(y.data_ptr()), B, H, W,
                                            ctypes.c_void_p(base), ws.numel() - (base - ws.data_ptr()), ctypes.c_void_p(stream)))
             self.last_launch_count = int(lib.hitsir_last_launch_count(h))
@@ -498,7 +521,7 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
         B, _, H, W = x_host.shape
         x_host = x_host.contiguous().float()
         if y_host is None:
-            y_host = torch.empty((B, self.in_chans, H * self.upscale, W * self.upscale), dtype=torch.float32, pin_memory=True)
+            y_host = torch.empty((B, self.in_chans, H * self.out_scale, W * self.out_scale), dtype=torch.float32, pin_memory=True)
         lib = _capi.load()
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
@@ -526,7 +549,7 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
             raise RuntimeError(f"expected {self.in_chans} channels, got {C}")
         device = x_u8.device
         x_u8 = x_u8.contiguous()
-        y = torch.empty((B, H * self.upscale, W * self.upscale, C), dtype=torch.uint8, device=device)
+        y = torch.empty((B, H * self.out_scale, W * self.out_scale, C), dtype=torch.uint8, device=device)
         lib = _capi.load()
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
@@ -535,7 +558,7 @@ class HiT_SIR(nn.Module, PyTorchModelHubMixin):
             ws = self._workspace(h, device, B, H, W)
             base = (ws.data_ptr() + 255) // 256 * 256
             dx = torch.empty((B, C, H, W), dtype=torch.float32, device=device)
-            dy = torch.empty((B, C, H * self.upscale, W * self.upscale), dtype=torch.float32, device=device)
+            dy = torch.empty((B, C, H * self.out_scale, W * self.out_scale), dtype=torch.float32, device=device)
             _capi.check(lib.hitsir_forward_u8(h, ctypes.c_void_p(x_u8.data_ptr()), ctypes.c_void_p(y.data_ptr()), B, H, W,
                                               ctypes.c_void_p(dx.data_ptr()), ctypes.c_void_p(dy.data_ptr()),
                                               ctypes.c_void_p(base), ws.numel() - (base - ws.data_ptr()), ctypes.c_void_p(stream)))

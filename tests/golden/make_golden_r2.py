@@ -47,12 +47,40 @@ BIG = [
 ]
 
 
-def build(flags, up, scale, mode, wseed, in_chans=3):
+def build(flags, up, scale, mode, wseed, in_chans=3, **extra):
     with contextlib.redirect_stdout(io.StringIO()):
-        m = HiT_SIR(*flags, upsampler=up, upscale=scale, in_chans=in_chans, **PRO).eval()
+        m = HiT_SIR(*flags, upsampler=up, upscale=scale, in_chans=in_chans, **PRO, **extra).eval()
     sd = fill_state_dict(m.state_dict(), wseed, mode)
+    if "absolute_pos_embed" in sd:             # make the embedding matter (its init-like fill is ~1e-3)
+        g = torch.Generator().manual_seed(wseed)
+        sd["absolute_pos_embed"] = torch.randn(sd["absolute_pos_embed"].shape, generator=g) * 0.5
     m.load_state_dict(sd, strict=True)
     return m, sd
+
+
+# constructor variants of section 8f-4: name, flags, upsampler, upscale, extra kwargs, (B,H,W), wseed, xseed
+VARIANTS = [
+    ("var_3conv_x2_direct_40x44", (False, True, True), "pixelshuffledirect", 2, dict(resi_connection="3conv"), (1, 40, 44), 31, 41),
+    ("var_ape_x2_direct_40x40", (False, True, True), "pixelshuffledirect", 2, dict(ape=True, img_size=40), (2, 40, 40), 32, 42),
+    ("var_noupsampler_40x44", (True, True, True), None, 4, dict(), (1, 40, 44), 33, 43),       # denoise mode: output is x-sized
+]
+
+
+def make_variants():
+    for name, flags, up, scale, extra, shape, wseed, xseed in VARIANTS:
+        m, sd = build(flags, up, scale, "stress", wseed, **extra)
+        x = synthetic_image(*shape, seed=xseed)
+        with torch.no_grad():
+            y = m(x)
+            with torch.autocast("cpu", dtype=torch.bfloat16):
+                yb = m(x).float()
+        sc = max(1.0, y.abs().max().item())
+        import math
+        yard = [(y - yb).abs().max().item() / sc, 10.0 * math.log10(1.0 / (((y - yb) / sc).double() ** 2).mean().item())]
+        meta = dict(flags=list(flags), upsampler=up, upscale=scale, mode="stress", wseed=wseed, shape=list(shape), xseed=xseed, extra=extra)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), y=y.numpy(), meta=np.array(repr(meta)), yardstick=np.array(yard),
+                            keys=np.array("\n".join(f"{k} {tuple(v.shape)}" for k, v in m.state_dict().items())))
+        print(f"{name}: y {tuple(y.shape)} mean {y.mean():.6f} std {y.std():.6f} keys {len(sd)} autocast-bf16 {yard}", flush=True)
 
 
 def crop_origins(hh, ww, c):
@@ -196,6 +224,8 @@ if __name__ == "__main__":
     what = sys.argv[1:] or ["small", "scc", "big"]
     if "yardstick" in what:
         make_yardstick()
+    if "variants" in what:
+        make_variants()
     if "small" in what:
         make_small()
     if "scc" in what:

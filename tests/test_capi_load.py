@@ -25,7 +25,7 @@ def test_header_symbols_exported():
 
 def test_config_struct_layout_matches_header():
     # 6 int32 + 16 + 16 int32 + 2 int32 + float + int32 + float + int32 + int32 + 16 float
-    assert ctypes.sizeof(_capi.HitsirConfig) == 4 * (6 + 16 + 16 + 2 + 1 + 1 + 1 + 1 + 1 + 16)
+    assert ctypes.sizeof(_capi.HitsirConfig) == 4 * (6 + 16 + 16 + 2 + 1 + 1 + 1 + 1 + 1 + 16 + 2)
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -50,7 +50,7 @@ def test_module_refuses_cpu_and_unsupported_configs():
     with pytest.raises(ValueError, match="not supported"):             # hit_sir_pro.py:1042
         hitsir_b200.HiT_SIR(True, True, True, **{**kw, "upsampler": "pixelshuffle", "upscale": 5})
     with pytest.raises(NotImplementedError):
-        hitsir_b200.HiT_SIR(True, True, True, **{**kw, "ape": True})
+        hitsir_b200.HiT_SIR(True, True, True, **{**kw, "patch_norm": False})
 
 
 def test_product_never_imports_oracle():

@@ -9,7 +9,7 @@ import hitsir_b200
 from oracle.weights import synthetic_image
 from tests.helpers import (GOLDEN_CASES, SCC_PART_BOUNDS, TAP_NAMES, YARD_CAP_PSNR_DB, YARD_FLOOR_MAXABS, assert_close, build_pair, load_golden,
                            load_yardstick, oracle_yardstick, psnr, rel_l2, tap_bound)
-from tests.test_oracle_golden import BIG_CASES, check_big
+from tests.test_oracle_golden import BIG_CASES, VARIANT_CASES, build_variant, check_big
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -79,6 +79,22 @@ def test_cuda_single_channel_matches_reference_golden():
     y = run_cuda(model, x)
     assert y.shape == (2, 1, 160, 176)
     assert_close(y, torch.from_numpy(g["y"]), meta["mode"], load_yardstick("gray_x4_direct_40x44"))
+
+
+@pytest.mark.parametrize("name", VARIANT_CASES)
+def test_cuda_matches_reference_constructor_variants(name):
+    """resi_connection='3conv', ape=True, upsampler=None against the unmodified reference; the bound is the reference's
+    own autocast-bf16 error stored with the fixture."""
+    g, meta = load_golden(name)
+    model, _ = build_variant(meta)
+    x = synthetic_image(*meta["shape"], seed=meta["xseed"])
+    y = run_cuda(model, x)
+    ref = torch.from_numpy(g["y"])
+    assert y.shape == ref.shape
+    assert_close(y, ref, meta["mode"], tuple(float(v) for v in g["yardstick"]))
+    if name.startswith("var_ape"):
+        with pytest.raises(Exception):                       # any other H*W cannot broadcast against absolute_pos_embed (:1294)
+            model.to(DEV)(synthetic_image(1, 40, 48, seed=1).to(DEV))
 
 
 def test_cuda_scc_parts_match_reference_golden():

@@ -77,6 +77,46 @@ def test_oracle_matches_reference_single_channel():
     assert (y - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
 
 
+VARIANT_CASES = ["var_3conv_x2_direct_40x44", "var_ape_x2_direct_40x40", "var_noupsampler_40x44"]
+
+
+def build_variant(meta):
+    return build_pair(meta["flags"], meta["upsampler"], meta["upscale"], meta["mode"], meta["wseed"], **meta["extra"])
+
+
+@pytest.mark.parametrize("name", VARIANT_CASES)
+def test_oracle_matches_reference_constructor_variants(name):
+    """resi_connection='3conv' (:913-918, :1224-1231), ape=True (:1187-1189, :1293-1294), upsampler=None (:1260-1262,
+    :1335-1344): same state_dict keys as the reference, oracle == reference output."""
+    g, meta = load_golden(name)
+    model, oracle = build_variant(meta)
+    assert "\n".join(f"{k} {tuple(v.shape)}" for k, v in model.state_dict().items()) == str(g["keys"])
+    x = synthetic_image(*meta["shape"], seed=meta["xseed"])
+    with torch.no_grad():
+        y = oracle(x)
+    ref = torch.from_numpy(g["y"])
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_save_pretrained_from_pretrained_round_trip(tmp_path):
+    """PyTorchModelHubMixin (hit_sir_pro.py:9, 1065): save_pretrained / from_pretrained on a local directory restores the weights
+    bit for bit (the constructor arguments are given again by the caller, exactly as with the reference class, whose signature has no
+    serialisable config either)."""
+    kw = dict(hitsir_b200.PRO_KWARGS)
+    kw.update(depths=[2, 2], num_heads=[6, 6], upsampler="pixelshuffledirect", upscale=2)
+    src = hitsir_b200.HiT_SIR(True, True, True, **kw)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.add_(torch.randn_like(p) * 0.01)
+    src.save_pretrained(str(tmp_path / "ckpt"))
+    dst = hitsir_b200.HiT_SIR.from_pretrained(str(tmp_path / "ckpt"), is_mult_size_conv_feat_extract=True, is_channel_spatial_attn=True,
+                                              is_fusion=True, **kw)
+    assert list(dst.state_dict()) == list(src.state_dict())
+    for k, v in src.state_dict().items():
+        assert torch.equal(v, dst.state_dict()[k]), k
+
+
 BIG_CASES = ["big_cfg3_tile576_x2ps_init", "big_cfg3_tile576_x2ps_stress", "big_cfg4_512_x4_init", "big_cfg4_512_x4_stress"]
 
 
