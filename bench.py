@@ -313,6 +313,43 @@ def run_cfg3(hitsir_b200, dev, world, rank):
             "steps": 3, "warmup": 2, "executed_tflops": round(GFLOP_PER_IMAGE["cfg3"] * len(origins) / (ms / 1e3) / 1e3, 1)}
 
 
+def run_cfg3_exact(hitsir_b200, dev, world, rank):
+    """BASELINE configs[2] as the reference itself runs it -- ONE whole 1920 x 1080 frame (test_experiment.py:75), x2 'pixelshuffle' --
+    sharded EXACTLY: row bands on 192-row boundaries, one per rank (at most 6 for 1080 rows), halo rows pushed over NVLink into the
+    neighbour's symmetric workspace, casa / UnionAttention statistics all-reduced (hitsir_b200/banded.py).  N = 1: the ordinary forward."""
+    import torch.distributed as dist
+    from hitsir_b200.banded import BandedSR, band_plan
+    model = make_model(hitsir_b200, "cfg3", dev)
+    g = torch.Generator(device=dev)
+    g.manual_seed(99)
+    frame = torch.rand(1, 3, 1080, 1920, device=dev, generator=g)     # the same frame on every rank
+    plan = band_plan(1080, world)
+    R = len(plan)
+    out = {}
+    if world > 1:
+        grp = dist.new_group(list(range(R)))
+        banded = BandedSR(model, group=grp) if rank < R else None
+
+        def step():
+            if banded is not None:
+                out["y"] = banded.forward(frame, dst_rank=0)
+    else:
+        def step():
+            out["y"] = model(frame)
+    with torch.no_grad():
+        for _ in range(2):
+            step()
+        ms, _ = timed_steps(step, lambda: None, 3, world, dev)
+    if rank == 0:
+        assert out["y"].shape == (1, 3, 2160, 3840) and torch.isfinite(out["y"]).all()
+    mp = 2160 * 3840 / 1e6
+    del model
+    torch.cuda.empty_cache()
+    return {"workload": f"cfg3 exact: the whole 1920x1080 frame, x2 pixelshuffle, {R} row band(s) {[r for _, r in plan]} over {world} GPU(s); "
+                        "halo rows over NVLink peer copies, statistics over NCCL, SR bands gathered to rank 0 inside the timed region",
+            "ms_per_frame": round(ms, 3), "value": round(mp / (ms / 1e3), 3), "unit": "MP/s (4K output)", "bands": R, "steps": 3, "warmup": 2}
+
+
 def run_ours(args):
     import torch.distributed as dist
     import hitsir_b200
@@ -480,6 +517,11 @@ def run_ours(args):
             line["cfg3"] = run_cfg3(hitsir_b200, dev, world, rank)
         except Exception as e:
             line["cfg3"] = {"error": f"{type(e).__name__}: {e}"}
+        torch.cuda.empty_cache()
+        try:
+            line["cfg3_exact"] = run_cfg3_exact(hitsir_b200, dev, world, rank)
+        except Exception as e:
+            line["cfg3_exact"] = {"error": f"{type(e).__name__}: {e}"}
     if rank == 0:
         if world == 1 and not args.no_extras:
             model._native.workspaces.clear()

@@ -103,6 +103,37 @@ HITSIR_API int hitsir_workspace_bytes(const HitsirHandle* h, int B, int H, int W
 HITSIR_API int hitsir_forward(HitsirHandle* h, const float* x, float* y, int B, int H, int W,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- exact multi-GPU sharding of ONE frame by rows --------------------------------------------------------------
+ * The reference always runs whole frames (test_experiment.py:75, experiments/experiment.py:743) and its casa pools (hit_sir_pro.py:348-349)
+ * and UnionAttention row / column statistics (:124-130) span the frame, so halo TILES are not the full-frame forward.  In band mode every
+ * GPU computes the rows [row0, row0 + H) of the frame -- band boundaries are multiples of 192 = lcm of the window sizes, so no window
+ * straddles two bands -- and the library asks the caller for exactly two kinds of exchange while it enqueues the forward:
+ *   halo:       the `halo_rows` rows above / below the `rows` core rows of a row-major buffer at workspace offset `ws_offset` must be
+ *               filled with the neighbour band's adjacent core rows (1 row for the 3x3 convolutions and the casa / UnionAttention
+ *               statistic maps, 2 rows of the FFN hidden map for the depthwise 5x5).  Every band lays its workspace out identically
+ *               (layout_h = the largest band height), so the neighbour's buffer is at the same offset of ITS workspace.
+ *   allreduce:  element-wise SUM of n_sum floats and MAX of n_max floats over all bands (casa global pools, UnionAttention column
+ *               statistics), in place.  Called whenever the pointer is non-NULL, also for a frame that is a single band (the
+ *               reduction is then the identity; callers use it to observe the statistics).
+ * Both run on the host thread that called hitsir_forward_band and must order their work on `stream`.  B = 1. */
+typedef int (*hitsir_halo_fn)(void* ctx, int64_t ws_offset, int64_t row_bytes, int32_t rows, int32_t halo_rows, void* stream);
+typedef int (*hitsir_allreduce_fn)(void* ctx, int64_t sum_offset, int64_t n_sum, int64_t max_offset, int64_t n_max, void* stream);
+typedef struct HitsirBand {
+  int32_t frame_h;       /* rows of the whole frame                                              */
+  int32_t row0;          /* first frame row of this band (a multiple of 192)                      */
+  int32_t layout_h;      /* largest band height of the frame: common workspace layout             */
+  int32_t has_top;       /* a neighbour band exists above / below                                 */
+  int32_t has_bottom;
+  hitsir_halo_fn halo;
+  hitsir_allreduce_fn allreduce;
+  void* ctx;
+} HitsirBand;
+HITSIR_API int hitsir_workspace_bytes_band(const HitsirHandle* h, int layout_h, int W, size_t* bytes);
+/* x_frame: the WHOLE LR frame (1, in_chans, frame_h, W) fp32 NCHW on this device (the 9x9 entry footprint reads across the band edge);
+ * y_band: (1, in_chans, s*H, s*W) = the band's rows of the output. */
+HITSIR_API int hitsir_forward_band(HitsirHandle* h, const float* x_frame, float* y_band, int H, int W, const HitsirBand* band,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* Same call with HOST buffers (pinned recommended): copies x host->device, runs the forward,
  * copies y device->host, all on `stream`; `dev_x`/`dev_y` are caller-provided device staging
  * buffers of B*C*H*W and B*C*sH*sW floats.  Returns after enqueueing; the caller synchronises. */

@@ -13,5 +13,6 @@ from .sharding import ShardedSR, PeerGather, tile_plan, stitch_tiles  # noqa: F4
 from .host_pipeline import HostPipeline  # noqa: F401
 from .metrics import mse_y, psnr_y, to_uint8_hwc  # noqa: F401
 from .graphed import GraphedForward  # noqa: F401
+from .banded import BandedSR, LocalBandedSR, band_plan  # noqa: F401
 
-__all__ = ["HiT_SIR", "PRO_KWARGS", "ShardedSR", "tile_plan", "stitch_tiles", "HostPipeline", "mse_y", "psnr_y", "to_uint8_hwc", "GraphedForward"]
+__all__ = ["HiT_SIR", "PRO_KWARGS", "ShardedSR", "tile_plan", "stitch_tiles", "HostPipeline", "mse_y", "psnr_y", "to_uint8_hwc", "GraphedForward", "BandedSR", "LocalBandedSR", "band_plan", "PeerGather"]

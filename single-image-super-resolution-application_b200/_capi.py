@@ -41,6 +41,15 @@ class HitsirConfig(C.Structure):
     ]
 
 
+HALO_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p)
+ALLREDUCE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p)
+
+
+class HitsirBand(C.Structure):
+    _fields_ = [("frame_h", C.c_int32), ("row0", C.c_int32), ("layout_h", C.c_int32), ("has_top", C.c_int32), ("has_bottom", C.c_int32),
+                ("halo", HALO_FN), ("allreduce", ALLREDUCE_FN), ("ctx", C.c_void_p)]
+
+
 SYMBOLS = {
     # name: (restype, argtypes)
     "hitsir_create": (C.c_int, [C.POINTER(HitsirConfig), C.POINTER(C.c_void_p)]),
@@ -52,6 +61,8 @@ SYMBOLS = {
     "hitsir_finalize_weights": (C.c_int, [C.c_void_p, C.c_void_p]),
     "hitsir_workspace_bytes": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
     "hitsir_forward": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "hitsir_workspace_bytes_band": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_size_t)]),
+    "hitsir_forward_band": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(HitsirBand), C.c_void_p, C.c_size_t, C.c_void_p]),
     "hitsir_forward_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_size_t, C.c_void_p]),
     "hitsir_forward_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,

@@ -92,7 +92,7 @@ conv3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int s = (int)(cnt % kAStages);
           mbar_wait(empty_bar(s), ((cnt / kAStages) & 1u) ^ 1u);
           mbar_expect_tx(full_bar(s), kATile);
-          tma_load_4d(sb + C::kOffA + s * kATile, &tmap_a, full_bar(s), 0, x0 + kx - 1, y0 - 1, b);
+          tma_load_4d(sb + C::kOffA + s * kATile, &tmap_a, full_bar(s), 0, x0 + kx - 1, y0 - 1 + p.a_y_off, b);
         }
       }
     }
@@ -212,7 +212,8 @@ int launch_bn(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb,
 // A: NHWC bf16 [B,H,W,64]; tb: packed weights [BN][576] with a {64, BN} box; BN = 64 -> out_bf16 [B,H,W,64], BN = 16 -> out_f32 NCHW
 int launch_conv3_c64(int BN, const GemmParams& p, const bf16* A, const CUtensorMap& tb, int num_sms, cudaStream_t st) {
   CUtensorMap ta, to;
-  if (make_tmap_nhwc(&ta, A, p.B, p.H, p.W, 64, 64, 16, 10)) return 1;
+  // band mode: A points at image row 0 of a buffer that has a_y_off valid halo rows above and below (engine.cu conv3)
+  if (make_tmap_nhwc(&ta, A - (size_t)p.a_y_off * p.W * 64, p.B, p.H + 2 * p.a_y_off, p.W, 64, 64, 16, 10)) return 1;
   to = ta;
   if (BN == 64) {
     if (make_tmap_nhwc(&to, p.out_bf16, p.B, p.H, p.W, 64, 64, 16, 8)) return 1;

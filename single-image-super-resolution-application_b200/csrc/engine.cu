@@ -502,6 +502,7 @@ struct Workspace {
   bf16* outsc = nullptr;                                 // bf16 [N,192]
   bf16 *H1 = nullptr, *H2 = nullptr;                     // bf16 [N,384] (contiguous: also G [N,768], A1|A2 fp32)
   float *havg, *hmax, *wavg, *wmax, *c_att, *h_att, *w_att;
+  float* red = nullptr;
   bf16* up = nullptr;                                    // upsampler scratch
   size_t up_bytes = 0;
   int nparts = 1;
@@ -515,9 +516,21 @@ struct Bump {
     off += count * sizeof(T);
     return p;
   }
+  // `count` elements with `halo` extra elements reserved in front of and behind them (band mode: rows exchanged with the neighbour
+  // bands); returns the first CORE element.  The halo is rounded up so that the core stays 256-byte aligned.
+  template <class T> T* take_ext(size_t count, size_t halo) {
+    const size_t hb = (halo * sizeof(T) + 255) & ~(size_t)255;
+    off = (off + 255) & ~(size_t)255;
+    T* p = base ? reinterpret_cast<T*>(base + off + hb) : nullptr;
+    off += 2 * hb + count * sizeof(T);
+    return p;
+  }
 };
 
-int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Workspace* ws) {
+// `halo`: 0 = ordinary forward; > 0 = band mode (exact row sharding of one frame): every buffer that a vertical stencil reads gets room
+// for halo rows above and below (at most 2 rows of its own row size), and H is the LARGEST band height of the frame so that every
+// rank / band lays its workspace out identically (peer addresses = own base + same offset)
+int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Workspace* ws, int halo = 0) {
   const HitsirConfig& c = h->cfg;
   const size_t N = (size_t)B * H * W;
   size_t np_max = N;
@@ -538,11 +551,17 @@ int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Wor
   ws->P = b.take<float>(N * kC);
   ws->Q = b.take<float>(N * kC);
   ws->S = b.take<float>(N * kC);
-  ws->xb0 = b.take<bf16>(N * kCp * 2);   // xb0 | xb1 contiguous
-  ws->xb1 = ws->xb0 ? ws->xb0 + N * kCp : nullptr;
+  const size_t hr = halo ? (size_t)W : 0;     // one halo row = W pixels
+  if (!halo) {
+    ws->xb0 = b.take<bf16>(N * kCp * 2);   // xb0 | xb1 contiguous
+    ws->xb1 = ws->xb0 ? ws->xb0 + N * kCp : nullptr;
+  } else {
+    ws->xb0 = b.take_ext<bf16>(N * kCp * 2, hr * kCp);       // also holds the im2col rows [N, <= 384]
+    ws->xb1 = b.take_ext<bf16>(N * kCp, hr * kCp);
+  }
   ws->T = b.take<bf16>(np_max * kCp);
-  ws->cavg = b.take<float>(np_max);
-  ws->cmax = b.take<float>(np_max);
+  ws->cavg = b.take_ext<float>(np_max, hr);
+  ws->cmax = b.take_ext<float>(np_max, hr);
   ws->nparts = 64;
   {
     const size_t np = (size_t)(ffn_tiles_per_image(H, W) > ws->nparts ? ffn_tiles_per_image(H, W) : ws->nparts);   // ffn_tail emits one partial per 8x16 tile
@@ -552,13 +571,14 @@ int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Wor
   ws->s1 = b.take<float>((size_t)B * kC);
   ws->s2 = b.take<float>((size_t)B * kC);
   ws->scc_dbg = b.take<float>((size_t)kSccDbgFloats);
-  ws->outsc = b.take<bf16>(N * kCp);
-  ws->H1 = b.take<bf16>(N * kHidp * 2);  // H1 | H2 contiguous
+  ws->outsc = b.take_ext<bf16>(N * kCp, hr * kCp);
+  ws->H1 = b.take_ext<bf16>(N * kHidp * 2, 2 * hr * kHidp);  // H1 | H2 contiguous
   ws->H2 = ws->H1 ? ws->H1 + N * kHidp : nullptr;
-  ws->havg = b.take<float>((size_t)B * kC * W);
-  ws->hmax = b.take<float>((size_t)B * kC * W);
-  ws->wavg = b.take<float>((size_t)B * kC * H);
-  ws->wmax = b.take<float>((size_t)B * kC * H);
+  ws->havg = b.take<float>((size_t)B * kC * W * 2);           // havg | hmax contiguous (one all-reduce payload each, adjacent)
+  ws->hmax = ws->havg ? ws->havg + (size_t)B * kC * W : nullptr;
+  ws->wavg = b.take_ext<float>((size_t)B * kC * H, halo ? kC : 0);
+  ws->wmax = b.take_ext<float>((size_t)B * kC * H, halo ? kC : 0);
+  ws->red = b.take<float>(2 * kCp);                           // band mode: [sum 180 | pad][max 180 | pad] all-reduce payload of the casa pools
   ws->c_att = b.take<float>(N);
   ws->h_att = b.take<float>((size_t)B * kC * W);
   ws->w_att = b.take<float>((size_t)B * kC * H);
@@ -570,6 +590,7 @@ int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Wor
     case HITSIR_UP_PIXELSHUFFLE: up = N * kNumFeat * (size_t)(1 + 4 + (s > 2 ? s * s : 0)); break;
     default: up = 0; break;
   }
+  if (halo) up += (size_t)16 * 2 * 4 * W * kNumFeat;          // halo rows of the (at most five) upsampler maps, each <= 2 rows of 4W pixels
   ws->up_bytes = up * sizeof(bf16);
   ws->up = b.take<bf16>(up);
   ws->bytes = (b.off + 255) & ~(size_t)255;
@@ -587,7 +608,36 @@ struct Fwd {
   Workspace ws;
   bool stopped = false;
   int stats_nparts = 0;      // > 0: casa statistics of the current stream were produced by the previous block's ffn_tail (partials per image)
+  // band mode (hitsir_forward_band): this call computes rows [row0, row0 + H) of a frame with Hf rows; halos come from the callbacks
+  const HitsirBand* band = nullptr;
+  void* ws_base = nullptr;
+  long long Nl = 0;          // pixels of the workspace LAYOUT (= N; band mode: B * layout_h * W, so that sub-buffers sit at the same offsets in every band)
+  int row0 = 0, Hf = 0;
+  bool top = false, bot = false;     // a neighbour band exists above / below
 };
+
+// Make the `halo` rows above and below the `rows` core rows of a row-major buffer valid before a vertical stencil reads them: rows
+// outside the frame are zero (the stencil's zero padding), rows of a neighbour band are fetched through the caller's exchange callback
+// (which runs on the host while the forward is being enqueued and must order its copies on `stream`).  No-op outside band mode.
+int fill_halo(Fwd& f, void* core, size_t row_bytes, int rows, int halo) {
+  if (f.band == nullptr) return 0;
+  uint8_t* c = reinterpret_cast<uint8_t*>(core);
+  if (!f.top) HITSIR_CHECK(cudaMemsetAsync(c - (size_t)halo * row_bytes, 0, (size_t)halo * row_bytes, f.st));
+  if (!f.bot) HITSIR_CHECK(cudaMemsetAsync(c + (size_t)rows * row_bytes, 0, (size_t)halo * row_bytes, f.st));
+  if (f.top || f.bot) {
+    const int rc = f.band->halo(f.band->ctx, (int64_t)(c - reinterpret_cast<uint8_t*>(f.ws_base)), (int64_t)row_bytes, rows, halo, f.st);
+    if (rc) { set_error("band halo exchange callback failed (%d)", rc); return HITSIR_ERR_INVALID; }
+  }
+  return 0;
+}
+// element-wise SUM of `n_sum` floats at `sum` and MAX of `n_max` floats at `mx` over all bands of the frame (in place)
+int band_allreduce(Fwd& f, float* sum, int64_t n_sum, float* mx, int64_t n_max) {
+  if (f.band == nullptr || f.band->allreduce == nullptr) return 0;     // a single band still reports its statistics when a callback is given
+  uint8_t* b0 = reinterpret_cast<uint8_t*>(f.ws_base);
+  const int rc = f.band->allreduce(f.band->ctx, (int64_t)(reinterpret_cast<uint8_t*>(sum) - b0), n_sum, (int64_t)(reinterpret_cast<uint8_t*>(mx) - b0), n_max, f.st);
+  if (rc) { set_error("band all-reduce callback failed (%d)", rc); return HITSIR_ERR_INVALID; }
+  return 0;
+}
 
 // returns 1 on error, sets f.stopped when the requested tap asked to stop
 int do_tap(Fwd& f, const char* name, const void* src, int is_bf16, int ld, long long rows, int cols, int perm = 0) {
@@ -672,9 +722,14 @@ int linear(Fwd& f, const char* cat, const GemmW& w, const bf16* A, long long M, 
   return run_gemm(f, cat, w, p, maps, tma);
 }
 
-// 3x3 conv over NHWC bf16 [B,H,W,Cpad]
+// 3x3 conv over NHWC bf16 [B,H,W,Cpad].  Band mode: the rows above / below A are made valid first (fill_halo: zeros at the frame
+// border, the neighbour band's rows otherwise) and the A tensor map starts one row above image row 0.
 int conv3(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, int W, int Cpad, GemmParams& p) {
   p.conv = 1; p.B = B; p.H = H; p.W = W;
+  if (f.band != nullptr) {
+    RUN(fill_halo(f, const_cast<bf16*>(A), (size_t)W * Cpad * sizeof(bf16), H, 1));
+    p.a_y_off = 1;
+  }
   p.tiles_x = cdiv(W, 16); p.tiles_y = cdiv(H, 8);
   p.m_tiles = B * p.tiles_x * p.tiles_y;
   p.cblocks = Cpad / 64;
@@ -691,7 +746,7 @@ int conv3(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, 
   CUtensorMap maps[5];
   const bool tma = tma_epilogue(f.h, w, p);
   if (!f.h->simt) {
-    if (make_tmap_nhwc(&maps[0], A, B, H, W, Cpad, 64, 16, 8)) return 1;
+    if (make_tmap_nhwc(&maps[0], A - (size_t)p.a_y_off * W * Cpad, B, H + 2 * p.a_y_off, W, Cpad, 64, 16, 8)) return 1;
     maps[1] = w.tm; maps[2] = maps[0]; maps[3] = maps[0]; maps[4] = maps[0];
     if (tma) {
       if (p.out_f32 && make_tmap_nhwc_t(&maps[2], p.out_f32, 4, B, H, W, p.n_real, p.ldf, 32, 16, 8)) return 1;
@@ -715,6 +770,10 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
   const int w = bw.win;
   SccGeom g;
   g.pg = PadGeom{f.B, f.H, f.W, round_up(f.H, w), round_up(f.W, w)};
+  if (f.band != nullptr) {     // frame-level geometry of the casa pools and the neighbours' statistic rows (kernels.cuh PadGeom)
+    g.pg.y0 = f.row0; g.pg.Hf = f.Hf; g.pg.Hpf = round_up(f.Hf, w);
+    g.pg.top = f.top ? 1 : 0; g.pg.bot = (f.bot && g.pg.Hp == f.H) ? 1 : 0;
+  }
   g.w = w; g.base = bw.base; g.r = bw.r; g.L = w * w; g.Lb = bw.base * bw.base;
   g.nWy = g.pg.Hp / w; g.nWx = g.pg.Wp / w; g.parts = 1;
   const long long Np = (long long)f.B * g.pg.Hp * g.pg.Wp;
@@ -731,7 +790,16 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
       nparts = ws.nparts;
       LAUNCH("sca_stats", 1, launch_sca_stats(xin, g.pg, ws.cavg, ws.cmax, ws.part_sum, ws.part_max, nparts, f.st));
     }
-    LAUNCH("sca_mlp", 1, launch_sca_mlp(ws.part_sum, ws.part_max, nparts, g.pg, bw.casa, ws.s1, ws.s2, f.st));
+    if (f.band != nullptr) {
+      // the global pools run over the whole padded FRAME: reduce this band's partials to one (sum, max) pair per channel, all-reduce
+      LAUNCH("sca_reduce", 1, launch_reduce_parts(ws.part_sum, ws.part_max, nparts, ws.red, ws.red + kCp, f.st));
+      RUN(band_allreduce(f, ws.red, kC, ws.red + kCp, kC));
+      LAUNCH("sca_mlp", 1, launch_sca_mlp(ws.red, ws.red + kCp, 1, g.pg, bw.casa, ws.s1, ws.s2, f.st));
+      RUN(fill_halo(f, ws.cavg, (size_t)f.W * sizeof(float), f.H, 1));      // the 3x3 gate convs read the neighbours' statistic rows
+      RUN(fill_halo(f, ws.cmax, (size_t)f.W * sizeof(float), f.H, 1));
+    } else {
+      LAUNCH("sca_mlp", 1, launch_sca_mlp(ws.part_sum, ws.part_max, nparts, g.pg, bw.casa, ws.s1, ws.s2, f.st));
+    }
   }
   f.stats_nparts = 0;
   LAUNCH("qkv_build", 1, launch_qkv_build(xin, g.pg, c.is_channel_spatial_attn, ws.cavg, ws.cmax, ws.s1, ws.s2, bw.casa, ws.T, f.st));
@@ -773,11 +841,14 @@ int forward_block(Fwd& f, int i, int j, float* xin, float* xout) {
     FfnStats fs; const FfnStats* fsp = nullptr;
     if (c.is_channel_spatial_attn && !need_shadow && !h->no_epilogue_stats) {
       const int wn = h->blocks[i][j + 1].win;
-      fs = FfnStats{ws.cavg, ws.cmax, ws.part_sum, ws.part_max, round_up(f.H, wn), round_up(f.W, wn)};
+      fs = FfnStats{ws.cavg, ws.cmax, ws.part_sum, ws.part_max, round_up(f.band ? f.Hf : f.H, wn), round_up(f.W, wn)};
       fsp = &fs;
     }
     bf16* shadow = (need_shadow && fsp == nullptr) ? ws.xb0 : nullptr;      // emitted by the kernel's statistics warp
-    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_mma, bw.w2_img, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, fsp, shadow, h->num_sms, f.st));
+    FfnBand fb{2, f.row0, f.Hf};
+    if (f.band != nullptr) RUN(fill_halo(f, ws.H1, (size_t)f.W * kHidp * sizeof(bf16), f.H, 2));   // the depthwise 5x5 reads two rows across the band edge
+    LAUNCH("ffn_tail", 1, launch_ffn_tail(ws.H1, bw.dw_mma, bw.w2_img, bw.fc2.b, bw.g2, bw.b2, xout, f.B, f.H, f.W, fsp, shadow, h->num_sms, f.st,
+                                          f.band ? &fb : nullptr));
     if (fsp != nullptr) f.stats_nparts = ffn_tiles_per_image(f.H, f.W);
     if (need_shadow && shadow == nullptr) LAUNCH("cast_shadow", 1, launch_cast_rows_bf16(xout, ws.xb0, f.N, f.st));
   } else {
@@ -802,8 +873,17 @@ int union_attention(Fwd& f, int u, const float* a, const float* b, float* out) {
   // UnionAttention.forward (:113-133) on X = a (+ b)
   HitsirHandle* h = f.h;
   Workspace& ws = f.ws;
-  LAUNCH("ua_stats", 2, launch_ua_stats(a, b, f.B, f.H, f.W, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, f.st));
-  LAUNCH("ua_small", 1, launch_ua_small_convs(f.B, f.H, f.W, h->ua[u].small, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, ws.c_att, ws.h_att, ws.w_att, f.st));
+  LAUNCH("ua_stats", 2, launch_ua_stats(a, b, f.B, f.H, f.W, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, f.st, f.band ? f.Hf : 0));
+  if (f.band != nullptr) {
+    // column statistics span the frame (all-reduce); the 3x3 convs over the (H, W) and (channel, H) planes read one row across the band edge
+    RUN(band_allreduce(f, ws.havg, (int64_t)kC * f.W, ws.hmax, (int64_t)kC * f.W));
+    RUN(fill_halo(f, ws.cavg, (size_t)f.W * sizeof(float), f.H, 1));
+    RUN(fill_halo(f, ws.cmax, (size_t)f.W * sizeof(float), f.H, 1));
+    RUN(fill_halo(f, ws.wavg, (size_t)kC * sizeof(float), f.H, 1));
+    RUN(fill_halo(f, ws.wmax, (size_t)kC * sizeof(float), f.H, 1));
+  }
+  LAUNCH("ua_small", 1, launch_ua_small_convs(f.B, f.H, f.W, h->ua[u].small, ws.cavg, ws.cmax, ws.havg, ws.hmax, ws.wavg, ws.wmax, ws.c_att, ws.h_att, ws.w_att, f.st,
+                                              f.top ? 1 : 0, f.bot ? 1 : 0));
   LAUNCH("ua_build", 1, launch_ua_build(f.B, f.H, f.W, ws.c_att, ws.h_att, ws.w_att, ws.outsc, f.st));
   GemmParams p;
   base_params(p, h->ua[u].conv_last);
@@ -818,7 +898,7 @@ int resi_3conv(Fwd& f, int idx, const char* cat, const bf16* in, const float* re
   Workspace& ws = f.ws;
   const int C4 = kC / 4;
   bf16* t1 = ws.outsc;
-  bf16* t2 = ws.outsc + f.N * 64;
+  bf16* t2 = ws.outsc + f.Nl * 64;
   GemmParams p;
   base_params(p, h->r3_a[idx]);
   p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = C4; p.out_bf16 = t1; p.ldb = 64;
@@ -840,7 +920,7 @@ int forward_impl(Fwd& f, const float* x, float* y) {
   GemmParams p;
   // ---- mean shift + shallow features (:1310-1311, :1315/1322/1328/1337) + patch_embed LayerNorm (:975-983)
   bf16* A0 = ws.xb0;   // [N, first_kp <= 384] aliases xb0|xb1, dead before the second GEMM writes xb0
-  LAUNCH("im2col", 1, launch_entry_im2col(x, A0, B, H, W, c.in_chans, h->first_f, h->first_kp, h->mean, c.img_range, f.st));
+  LAUNCH("im2col", 1, launch_entry_im2col(x, A0, B, H, W, c.in_chans, h->first_f, h->first_kp, h->mean, c.img_range, f.st, f.row0, f.band ? f.Hf : 0));
   const float* pe_g = P(h, "patch_embed.norm.weight");
   const float* pe_b = P(h, "patch_embed.norm.bias");
   if (c.is_mult_size_conv_feat_extract) {
@@ -912,6 +992,8 @@ int forward_impl(Fwd& f, const float* x, float* y) {
   RUN(do_inject(f, "fused", nullptr, F, N));
   // ---- reconstruction (:1313-1340)
   const int s = c.upscale;
+  const long long Nl = f.Nl;                                               // layout pixels (band mode: identical buffer offsets in every band)
+  const size_t gap = f.band ? (size_t)2 * 4 * W * kNumFeat : 0;           // room for the halo rows of the upsampler maps
   auto last_params = [&](GemmParams& q, const GemmW& w, int ps) {
     base_params(q, w);
     q.epi = EPI_SHUFFLE_NCHW; q.ps = ps; q.n_real = c.in_chans * ps * ps; q.shuf_c = c.in_chans;
@@ -920,11 +1002,11 @@ int forward_impl(Fwd& f, const float* x, float* y) {
     q.out_f32 = y;
   };
   if (c.upsampler == HITSIR_UP_NEAREST_CONV) {
-    bf16* U0 = ws.up;
-    bf16* U0up = U0 + N * kNumFeat;
-    bf16* U1 = U0up + 4 * N * kNumFeat;
-    bf16* U1up = U1 + 4 * N * kNumFeat;
-    bf16* U2 = U1up + 16 * N * kNumFeat;
+    bf16* U0 = ws.up + gap;
+    bf16* U0up = U0 + Nl * kNumFeat + gap;
+    bf16* U1 = U0up + 4 * Nl * kNumFeat + gap;
+    bf16* U1up = U1 + 4 * Nl * kNumFeat + gap;
+    bf16* U2 = U1up + 16 * Nl * kNumFeat + gap;
     bf16* U3 = U1up;
     base_params(p, h->conv_before_upsample);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.01f; p.n_real = kNumFeat; p.out_bf16 = U0; p.ldb = kNumFeat;   // nn.LeakyReLU() default slope (:1251)
@@ -947,9 +1029,9 @@ int forward_impl(Fwd& f, const float* x, float* y) {
     last_params(p, h->conv_last, 1);
     RUN(conv3(f, "conv_last", h->conv_last, U3, B, 4 * H, 4 * W, kNumFeat, p));
   } else if (c.upsampler == HITSIR_UP_PIXELSHUFFLE) {
-    bf16* U0 = ws.up;
-    bf16* Ua = U0 + N * kNumFeat;
-    bf16* Ub = Ua + 4 * N * kNumFeat;
+    bf16* U0 = ws.up + gap;
+    bf16* Ua = U0 + Nl * kNumFeat + gap;
+    bf16* Ub = Ua + 4 * Nl * kNumFeat + gap;
     base_params(p, h->conv_before_upsample);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.01f; p.n_real = kNumFeat; p.out_bf16 = U0; p.ldb = kNumFeat;
     RUN(conv3(f, "conv_before_upsample", h->conv_before_upsample, F, B, H, W, kCp, p));
@@ -1088,7 +1170,7 @@ HITSIR_API int hitsir_forward(HitsirHandle* h, const float* x, float* y, int B, 
     if ((long long)B * H * W * 16 >= 2147483647LL) { set_error("input too large: B*H*W*16 must be < 2^31"); return HITSIR_ERR_UNSUPPORTED; }
   }
   Fwd f;
-  f.h = h; f.st = (cudaStream_t)stream; f.B = B; f.H = H; f.W = W; f.N = (long long)B * H * W;
+  f.h = h; f.st = (cudaStream_t)stream; f.B = B; f.H = H; f.W = W; f.N = (long long)B * H * W; f.Nl = f.N;
   int rc = layout_workspace(h, B, H, W, workspace, &f.ws);
   if (rc) return rc;
   if (((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned"); return HITSIR_ERR_WORKSPACE; }
@@ -1096,6 +1178,44 @@ HITSIR_API int hitsir_forward(HitsirHandle* h, const float* x, float* y, int B, 
   h->launches = 0;
   rc = forward_impl(f, x, y);
   return rc;
+}
+
+HITSIR_API int hitsir_workspace_bytes_band(const HitsirHandle* h, int layout_h, int W, size_t* bytes) {
+  if (!h || !bytes || layout_h < 1 || W < 1) { set_error("hitsir_workspace_bytes_band: bad argument"); return HITSIR_ERR_INVALID; }
+  Workspace ws;
+  int rc = layout_workspace(h, 1, layout_h, W, nullptr, &ws, 1);
+  if (rc) return rc;
+  *bytes = ws.bytes;
+  return 0;
+}
+
+HITSIR_API int hitsir_forward_band(HitsirHandle* h, const float* x_frame, float* y_band, int H, int W, const HitsirBand* band, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
+  if (!h || !x_frame || !y_band || !workspace || !band) { set_error("hitsir_forward_band: null argument"); return HITSIR_ERR_INVALID; }
+  if (!h->finalized) { set_error("hitsir_forward_band: weights not finalized"); return HITSIR_ERR_WEIGHTS; }
+  if ((band->has_top || band->has_bottom) && (!band->halo || !band->allreduce)) { set_error("hitsir_forward_band: exchange callbacks missing"); return HITSIR_ERR_INVALID; }
+  if (H < 1 || H > band->layout_h || band->row0 < 0 || band->row0 + H > band->frame_h) { set_error("hitsir_forward_band: band rows [%d, %d) do not fit frame_h %d / layout_h %d", band->row0, band->row0 + H, band->frame_h, band->layout_h); return HITSIR_ERR_INVALID; }
+  if (band->row0 % 192 != 0 || (band->has_bottom && H % 192 != 0)) {
+    set_error("hitsir_forward_band: band boundaries must be multiples of 192 (lcm of the window sizes): row0 %d, rows %d", band->row0, H);
+    return HITSIR_ERR_INVALID;
+  }
+  if (h->cfg.ape_tokens > 0) { set_error("hitsir_forward_band: ape=True is not supported in band mode"); return HITSIR_ERR_UNSUPPORTED; }
+  if (h->cfg.upsampler == HITSIR_UP_NONE) { set_error("hitsir_forward_band: upsampler=None (same-size output added to the input) is not supported in band mode"); return HITSIR_ERR_UNSUPPORTED; }
+  if (h->tap.dst != nullptr || h->inject.src != nullptr) { set_error("hitsir_forward_band: taps / injections are not supported in band mode"); return HITSIR_ERR_UNSUPPORTED; }
+  Fwd f;
+  f.h = h; f.st = (cudaStream_t)stream; f.B = 1; f.H = H; f.W = W; f.N = (long long)H * W; f.Nl = (long long)band->layout_h * W;
+  f.band = band; f.ws_base = workspace; f.row0 = band->row0; f.Hf = band->frame_h; f.top = band->has_top != 0; f.bot = band->has_bottom != 0;
+  int rc = layout_workspace(h, 1, band->layout_h, W, workspace, &f.ws, 1);
+  if (rc) return rc;
+  if (((uintptr_t)workspace & 255) != 0) { set_error("workspace must be 256-byte aligned"); return HITSIR_ERR_WORKSPACE; }
+  if (f.ws.bytes > workspace_bytes) { set_error("workspace too small: need %zu bytes, got %zu", f.ws.bytes, workspace_bytes); return HITSIR_ERR_WORKSPACE; }
+  // the reference pads the FRAME: a band of the last rows may be shorter than its own reflect padding only if the frame is
+  for (int j = 0; j < h->cfg.depths[0]; ++j) {
+    const int w = win_of(h->cfg, j), pad = round_up(H, w) - H;
+    if (pad >= H) { set_error("band of %d rows is shorter than the reflect padding (%d) of window %d: merge it with its neighbour", H, pad, w); return HITSIR_ERR_INPUT_TOO_SMALL; }
+  }
+  h->launches = 0;
+  return forward_impl(f, x_frame, y_band);
 }
 
 HITSIR_API int hitsir_forward_host(HitsirHandle* h, const float* host_x, float* host_y, int B, int H, int W, float* dev_x, float* dev_y,

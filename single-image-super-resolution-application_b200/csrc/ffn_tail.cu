@@ -58,6 +58,9 @@ struct Params {
   const uint32_t* dw_tbl;                    // tap rows [384][28] (launch_pack_dw_mma)
   const uint8_t* w2_img;                     // fc2 weights as six SWIZZLE_128B operand images [192 rows x 64 k] (launch_pack_w2_image)
   bf16* shadow;                              // optional bf16 copy of the updated stream [B*H*W][192] (pads 0) for the RHTB conv that follows (:934)
+  // band mode (exact multi-GPU sharding of one frame by rows, engine.cu): the h1 map has h1_y_off valid halo rows above row 0, and the
+  // reflect multiplicities of the casa pools are those of the whole frame (row yg0 + y of a frame with Hf rows)
+  int h1_y_off, yg0, Hf;
 };
 __device__ __forceinline__ int reflect_mult(int i, int n, int np) { return 1 + ((i >= 2 * (n - 1) - (np - 1) && i <= n - 2) ? 1 : 0); }
 
@@ -148,7 +151,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
           const uint32_t u = (uint32_t)(it * 3 + (k >> 1));
           mbar_wait(halo_empty(h), (u & 1u) ^ 1u);
           mbar_expect_tx(halo_full(h), kHalo + kDwTbl);
-          tma_load_4d(sb + kOffHalo + h * kHaloStage, &tm_h1, halo_full(h), k * 64, x0 - 2, y0 - 2, b);
+          tma_load_4d(sb + kOffHalo + h * kHaloStage, &tm_h1, halo_full(h), k * 64, x0 - 2, y0 - 2 + p.h1_y_off, b);
           bulk_load(sb + kOffHalo + h * kHaloStage + kHalo, p.dw_tbl + (size_t)k * (kDwTbl / 4), kDwTbl, halo_full(h));   // 64 contiguous tap rows
           mbar_wait(w_empty(h), (u & 1u) ^ 1u);
           mbar_expect_tx(w_full(h), kWStage);
@@ -191,7 +194,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
         int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
         for (int rr = lane; rr < 128; rr += 32) {
           const int y = y0 + (rr >> 4), x = x0 + (rr & 15);
-          s_mult[rr] = (y < p.H && x < p.W) ? (float)(reflect_mult(y, p.H, p.Hp) * reflect_mult(x, p.W, p.Wp)) : 0.f;
+          s_mult[rr] = (y < p.H && x < p.W) ? (float)(reflect_mult(y + p.yg0, p.Hf, p.Hp) * reflect_mult(x, p.W, p.Wp)) : 0.f;
         }
         __syncwarp();
         for (int j = 0; j < 6; ++j, ++u) {
@@ -494,7 +497,8 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
 // h1: bf16 [B,H,W,384]; dw_tbl_mma: depthwise tap rows (launch_pack_dw_mma); w2_img: fc2 operand images (launch_pack_w2_image);
 // x: fp32 residual stream [B,H,W,180], updated in place
 int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const uint8_t* w2_img, const float* b2, const float* gamma,
-                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, bf16* shadow, int num_sms, cudaStream_t st) {
+                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, bf16* shadow, int num_sms, cudaStream_t st,
+                    const FfnBand* band) {
   static unsigned long long configured = 0;
   if (ensure_dynamic_smem(ffn_tail_kernel, kSmemBytes, &configured)) return 1;
   Params p;
@@ -508,8 +512,11 @@ int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const uint8_t* w
   p.shadow = stats == nullptr ? shadow : nullptr;          // the statistics warp does one or the other
   if (stats != nullptr) { p.cavg = stats->cavg; p.cmax = stats->cmax; p.part_sum = stats->part_sum; p.part_max = stats->part_max; p.Hp = stats->Hp; p.Wp = stats->Wp; }
   p.dw_tbl = dw_tbl_mma; p.w2_img = w2_img;
+  p.h1_y_off = band ? band->halo : 0; p.yg0 = band ? band->yg0 : 0; p.Hf = band ? band->Hf : H;
+  if (band && B != 1) { set_error("launch_ffn_tail: band mode needs B == 1"); return 1; }
   CUtensorMap tm_h1, tm_x;
-  if (make_tmap_nhwc(&tm_h1, h1, B, H, W, kHidp, 64, kPW, kPH)) return 1;               // SWIZZLE_128B halo boxes, zero fill outside the image
+  // SWIZZLE_128B halo boxes, zero fill outside the image; band mode: the map starts h1_y_off rows above image row 0 (rows filled by the neighbour)
+  if (make_tmap_nhwc(&tm_h1, h1 - (size_t)p.h1_y_off * W * kHidp, B, H + 2 * p.h1_y_off, W, kHidp, 64, kPW, kPH)) return 1;
   if (make_tmap_nhwc_t(&tm_x, x, 4, B, H, W, kC, kC, 32, 16, 8)) return 1;
   const int grid = p.total < num_sms ? p.total : num_sms;
   ffn_tail_kernel<<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_x, p);

@@ -30,6 +30,7 @@ struct GemmParams {
   int num_kb;        // K / 64
   int b_resident;    // linear, K <= 192, grid % n_tiles == 0: the CTA's weight tile is loaded once and stays in shared memory (umma_gemm_tma.cu)
   int cblocks;       // conv: Cin_pad / 64
+  int a_y_off;       // conv: rows of valid halo ABOVE image row 0 in the A tensor map (band mode: the map covers [-a_y_off, H + a_y_off))
   // epilogue
   int epi, act;
   int n_real;        // number of meaningful output columns (of n_tiles*BN)

@@ -25,7 +25,7 @@ __device__ __forceinline__ int reflect_mult(int i, int n, int np) { return 1 + (
 constexpr int kImSeg = 64;
 constexpr int kImMaxWin = 3 * 9 * (kImSeg + 8);
 __global__ void __launch_bounds__(256) entry_im2col_kernel(const float* __restrict__ x, bf16* __restrict__ a0, int B, int H, int W, int in_ch, int f, int Kp,
-                                                            float m0, float m1, float m2, float img_range, int nseg) {
+                                                            float m0, float m1, float m2, float img_range, int nseg, int yb0, int Hf) {
   __shared__ bf16 tile[kImMaxWin];
   __shared__ uint16_t ktab[512];
   const int seg = blockIdx.x % nseg; const int t2 = blockIdx.x / nseg;
@@ -39,11 +39,11 @@ __global__ void __launch_bounds__(256) entry_im2col_kernel(const float* __restri
   }
   for (int i = threadIdx.x; i < in_ch * f * wcols; i += blockDim.x) {
     const int cx = i % wcols; const int r2 = i / wcols; const int ry = r2 % f, c = r2 / f;
-    const int yy = y + ry - half, xx = x0 + cx - half;
+    const int yy = yb0 + y + ry - half, xx = x0 + cx - half;              // frame row (band mode: yb0 = first frame row of the band)
     float val = 0.f;
-    if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+    if (yy >= 0 && yy < Hf && xx >= 0 && xx < W) {
       const float mean = (in_ch == 3) ? (c == 0 ? m0 : (c == 1 ? m1 : m2)) : 0.f;
-      val = (__ldg(x + (((long long)b * in_ch + c) * H + yy) * W + xx) - mean) * img_range;
+      val = (__ldg(x + (((long long)b * in_ch + c) * Hf + yy) * W + xx) - mean) * img_range;
     }
     tile[i] = __float2bfloat16(val);
   }
@@ -339,7 +339,7 @@ __global__ void __launch_bounds__(256) sca_stats_kernel(const float* __restrict_
       const int pp = pp0 + u;
       if (pp >= p1) break;
       const int y = pp / g.W, xw = pp - y * g.W;
-      const float mult = (float)(reflect_mult(y, g.H, g.Hp) * reflect_mult(xw, g.W, g.Wp));
+      const float mult = (float)(reflect_mult(y + g.y0, g.Hf > 0 ? g.Hf : g.H, g.Hf > 0 ? g.Hpf : g.Hp) * reflect_mult(xw, g.W, g.Wp));
       float s = 0.f, m = -INFINITY;
 #pragma unroll
       for (int i = 0; i < 6; ++i) {
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(768) sca_mlp_kernel(const float* __restrict__ 
   }
   __syncthreads();
   if (grp == 0 && c < kC) {
-    avg[c] = (((ps[0][c] + ps[1][c]) + ps[2][c]) + ps[3][c]) / (float)(g.Hp * g.Wp);
+    avg[c] = (((ps[0][c] + ps[1][c]) + ps[2][c]) + ps[3][c]) / (float)((g.Hf > 0 ? g.Hpf : g.Hp) * g.Wp);
     mx[c] = fmaxf(fmaxf(pm[0][c], pm[1][c]), fmaxf(pm[2][c], pm[3][c]));
   }
   __syncthreads();
@@ -605,8 +605,10 @@ __global__ void __launch_bounds__(128) qkv_casa_mma_kernel(const float* __restri
       const int v = i / (3 * (kMmaRun + 2)), r2 = i - v * 3 * (kMmaRun + 2);
       const int rr = r2 / (kMmaRun + 2), cc = r2 - rr * (kMmaRun + 2);
       const int yy = yp + rr - 1, xx = xs0 + cc - 1;
-      const bool ok = yy >= 0 && yy < g.Hp && xx >= 0 && xx < g.Wp;
-      const int src = ok ? reflect_src(yy, g.H) * g.W + reflect_src(xx, g.W) : 0;
+      // band mode: row -1 / row Hp of an interior band boundary is the neighbour's statistic row (halo rows of the maps), not zero padding
+      const bool inr = yy >= 0 && yy < g.Hp;
+      const bool ok = (inr || (yy == -1 && g.top) || (yy == g.Hp && g.bot)) && xx >= 0 && xx < g.Wp;
+      const int src = ok ? (inr ? reflect_src(yy, g.H) : (yy < 0 ? -1 : g.H)) * g.W + reflect_src(xx, g.W) : 0;
       sw[i] = ok ? (v == 0 ? ca : cm)[src] : 0.f;
     }
     __syncthreads();                                       // windows written; the previous run's output tile has been copied out
@@ -712,13 +714,13 @@ __global__ void __launch_bounds__(256) ua_rows_kernel(const float* __restrict__ 
     float s = 0.f, m = -INFINITY;
 #pragma unroll
     for (int wv = 0; wv < 8; ++wv) { s += s_sum[wv][c]; m = fmaxf(m, s_max[wv][c]); }
-    wavg[((long long)b * kC + c) * H + y] = s / (float)W;
-    wmax[((long long)b * kC + c) * H + y] = m;
+    wavg[((long long)b * H + y) * kC + c] = s / (float)W;
+    wmax[((long long)b * H + y) * kC + c] = m;
   }
 }
 
 __global__ void __launch_bounds__(192) ua_cols_kernel(const float* __restrict__ a, const float* __restrict__ bsrc, int B, int H, int W,
-                                                      float* __restrict__ havg, float* __restrict__ hmax) {
+                                                      float* __restrict__ havg, float* __restrict__ hmax, int Hf) {
   const int b = blockIdx.x / W, xw = blockIdx.x - b * W;
   const int c = threadIdx.x;
   if (c >= kC) return;
@@ -728,23 +730,25 @@ __global__ void __launch_bounds__(192) ua_cols_kernel(const float* __restrict__ 
     float v = a[off]; if (bsrc != nullptr) v += bsrc[off];
     s += v; m = fmaxf(m, v);
   }
-  havg[((long long)b * kC + c) * W + xw] = s / (float)H;
+  havg[((long long)b * kC + c) * W + xw] = s / (float)Hf;       // band mode: this band's share of the frame mean (all-reduced by SUM)
   hmax[((long long)b * kC + c) * W + xw] = m;
 }
 
 // 3x3 conv 2->1 on a (rows x cols) plane pair, zero padded.  plane layouts: avg/max [B][rows][cols]
+// top / bot: row -1 / row `rows` exists (halo row of the neighbour band); tr: the filter is applied transposed (plane stored [cols][rows] ...)
 __device__ __forceinline__ float conv2to1(const float* __restrict__ pa, const float* __restrict__ pm, int rows, int cols, int rr, int cc,
-                                          const float* __restrict__ w, float bias) {
+                                          const float* __restrict__ w, float bias, int top = 0, int bot = 0, bool tr = false) {
   float acc = bias;
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     const int r2 = rr + ky - 1;
-    if (r2 < 0 || r2 >= rows) continue;
+    if ((r2 < 0 && !(top && r2 == -1)) || (r2 >= rows && !(bot && r2 == rows))) continue;
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int c2 = cc + kx - 1;
       if (c2 < 0 || c2 >= cols) continue;
-      acc += w[ky * 3 + kx] * pa[(long long)r2 * cols + c2] + w[9 + ky * 3 + kx] * pm[(long long)r2 * cols + c2];
+      const int wi = tr ? kx * 3 + ky : ky * 3 + kx;
+      acc += w[wi] * pa[(long long)r2 * cols + c2] + w[9 + wi] * pm[(long long)r2 * cols + c2];
     }
   }
   return acc;
@@ -752,22 +756,23 @@ __device__ __forceinline__ float conv2to1(const float* __restrict__ pa, const fl
 
 __global__ void ua_small_convs_kernel(int B, int H, int W, UaW w, const float* __restrict__ cavg, const float* __restrict__ cmax,
                                       const float* __restrict__ havg, const float* __restrict__ hmax, const float* __restrict__ wavg,
-                                      const float* __restrict__ wmax, float* __restrict__ c_att, float* __restrict__ h_att, float* __restrict__ w_att) {
+                                      const float* __restrict__ wmax, float* __restrict__ c_att, float* __restrict__ h_att, float* __restrict__ w_att,
+                                      int top, int bot) {
   const long long n1 = (long long)B * H * W, n2 = (long long)B * kC * W, n3 = (long long)B * kC * H;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n1 + n2 + n3; idx += (long long)gridDim.x * blockDim.x) {
     if (idx < n1) {                 // conv1 over the (H, W) plane                       (:120-122)
       const int b = (int)(idx / (H * W)); const int rem = (int)(idx - (long long)b * H * W);
-      c_att[idx] = conv2to1(cavg + (long long)b * H * W, cmax + (long long)b * H * W, H, W, rem / W, rem % W, w.c1_w, w.c1_b[0]);
+      c_att[idx] = conv2to1(cavg + (long long)b * H * W, cmax + (long long)b * H * W, H, W, rem / W, rem % W, w.c1_w, w.c1_b[0], top, bot);
     } else if (idx < n1 + n2) {     // conv2 over the (channel, W) plane                 (:124-126)
       const long long i = idx - n1;
       const int b = (int)(i / (kC * W)); const int rem = (int)(i - (long long)b * kC * W);
       h_att[((long long)b * W + rem % W) * kC + rem / W] =      // stored [b][x][c] (channel fastest) for ua_build
           conv2to1(havg + (long long)b * kC * W, hmax + (long long)b * kC * W, kC, W, rem / W, rem % W, w.c2_w, w.c2_b[0]);
-    } else {                        // conv3 over the (channel, H) plane                 (:128-130)
+    } else {                        // conv3 over the (channel, H) plane                 (:128-130); the plane is stored [y][c], filter transposed
       const long long i = idx - n1 - n2;
       const int b = (int)(i / (kC * H)); const int rem = (int)(i - (long long)b * kC * H);
-      w_att[((long long)b * H + rem % H) * kC + rem / H] =      // stored [b][y][c]
-          conv2to1(wavg + (long long)b * kC * H, wmax + (long long)b * kC * H, kC, H, rem / H, rem % H, w.c3_w, w.c3_b[0]);
+      w_att[(long long)b * H * kC + rem] =                      // stored [b][y][c]
+          conv2to1(wavg + (long long)b * kC * H, wmax + (long long)b * kC * H, H, kC, rem / kC, rem % kC, w.c3_w, w.c3_b[0], top, bot, true);
     }
   }
 }
@@ -825,12 +830,13 @@ inline int grid_for(long long total, int block) {
 
 }  // namespace
 
-int launch_entry_im2col(const float* x, bf16* a0, int B, int H, int W, int in_ch, int f, int Kp, const float* mean3, float img_range, cudaStream_t st) {
+int launch_entry_im2col(const float* x, bf16* a0, int B, int H, int W, int in_ch, int f, int Kp, const float* mean3, float img_range, cudaStream_t st,
+                        int y0, int Hf) {
   if (in_ch > 3 || f > 9 || Kp > 512 || Kp % 8 != 0) { set_error("launch_entry_im2col: footprint %d x %d x %d / Kp %d not supported", f, f, in_ch, Kp); return 1; }
   const int nseg = (W + kImSeg - 1) / kImSeg;
   const long long ctas = (long long)B * H * nseg;
   if (ctas > 2147483647LL) { set_error("launch_entry_im2col: too many rows"); return 1; }
-  entry_im2col_kernel<<<(unsigned)ctas, 256, 0, st>>>(x, a0, B, H, W, in_ch, f, Kp, mean3[0], mean3[1], mean3[2], img_range, nseg);
+  entry_im2col_kernel<<<(unsigned)ctas, 256, 0, st>>>(x, a0, B, H, W, in_ch, f, Kp, mean3[0], mean3[1], mean3[2], img_range, nseg, y0, Hf > 0 ? Hf : H);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
@@ -908,6 +914,22 @@ int launch_sca_stats(const float* x, PadGeom g, float* cavg, float* cmax, float*
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
+__global__ void reduce_parts_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_max, int nparts, float* __restrict__ out_sum,
+                                    float* __restrict__ out_max) {
+  const int c = threadIdx.x;
+  if (c >= kC) return;
+  // same association as sca_mlp_kernel (four strided groups merged in order), so that a frame run as ONE band reproduces the ordinary forward bit for bit
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, m = -INFINITY;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    for (int p = g; p < nparts; p += 4) { s[g] += part_sum[(long long)p * kC + c]; m = fmaxf(m, part_max[(long long)p * kC + c]); }
+  out_sum[c] = ((s[0] + s[1]) + s[2]) + s[3]; out_max[c] = m;
+}
+int launch_reduce_parts(const float* part_sum, const float* part_max, int nparts, float* out_sum, float* out_max, cudaStream_t st) {
+  reduce_parts_kernel<<<1, 192, 0, st>>>(part_sum, part_max, nparts, out_sum, out_max);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
 int launch_sca_mlp(const float* part_sum, const float* part_max, int nparts, PadGeom g, CasaW w, float* s1, float* s2, cudaStream_t st) {
   sca_mlp_kernel<<<g.B, 768, 0, st>>>(part_sum, part_max, nparts, g, w, s1, s2);
   HITSIR_CHECK(cudaGetLastError());
@@ -944,17 +966,17 @@ int launch_pack_casa_bfrag(CasaW w, uint32_t* img, cudaStream_t st) {
   return 0;
 }
 int launch_ua_stats(const float* a, const float* b, int B, int H, int W, float* cavg, float* cmax, float* havg, float* hmax, float* wavg, float* wmax,
-                    cudaStream_t st) {
+                    cudaStream_t st, int Hf) {
   ua_rows_kernel<<<B * H, 256, 0, st>>>(a, b, B, H, W, cavg, cmax, wavg, wmax);
   HITSIR_CHECK(cudaGetLastError());
-  ua_cols_kernel<<<B * W, 192, 0, st>>>(a, b, B, H, W, havg, hmax);
+  ua_cols_kernel<<<B * W, 192, 0, st>>>(a, b, B, H, W, havg, hmax, Hf > 0 ? Hf : H);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
 int launch_ua_small_convs(int B, int H, int W, UaW w, const float* cavg, const float* cmax, const float* havg, const float* hmax, const float* wavg,
-                          const float* wmax, float* c_att, float* h_att, float* w_att, cudaStream_t st) {
+                          const float* wmax, float* c_att, float* h_att, float* w_att, cudaStream_t st, int top, int bot) {
   const long long total = (long long)B * H * W + (long long)B * kC * W + (long long)B * kC * H;
-  ua_small_convs_kernel<<<grid_for(total, 256), 256, 0, st>>>(B, H, W, w, cavg, cmax, havg, hmax, wavg, wmax, c_att, h_att, w_att);
+  ua_small_convs_kernel<<<grid_for(total, 256), 256, 0, st>>>(B, H, W, w, cavg, cmax, havg, hmax, wavg, wmax, c_att, h_att, w_att, top, bot);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

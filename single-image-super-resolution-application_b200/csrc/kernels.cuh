@@ -14,8 +14,9 @@ constexpr int kHidp = 384;
 
 // ---- glue.cu ---------------------------------------------------------------------------
 // NCHW fp32 image -> im2col rows [N, Kp] bf16 of ((x - mean) * img_range), footprint f x f, zero padded
+// band mode: rows [y0, y0 + H) of a frame with Hf rows are converted (x is the whole frame); y0 = 0, Hf = 0 -> the whole image
 int launch_entry_im2col(const float* x, bf16* a0, int B, int H, int W, int in_ch, int f, int Kp,
-                        const float* mean3, float img_range, cudaStream_t st);
+                        const float* mean3, float img_range, cudaStream_t st, int y0 = 0, int Hf = 0);
 // LayerNorm over rows of fp32 [N,180] -> bf16 [N,192] (pad zero) and/or fp32 [N,180]
 // add (optional): fp32 [add_rows, 180] added after the normalisation, row index modulo add_rows (absolute position embedding)
 int launch_ln_rows(const float* x, const float* gamma, const float* beta, bf16* out_bf16, float* out_f32, long long N, cudaStream_t st,
@@ -34,8 +35,11 @@ int launch_pack_dw_mma(const float* dw_tbl, uint32_t* out, cudaStream_t st);
 // w2_img (launch_pack_w2_image): the packed fc2 weights [192][384] re-laid as six contiguous SWIZZLE_128B operand images [192 rows x 64 k]
 // (24 KB each), so that a slice is one bulk copy instead of 192 TMA rows
 int launch_pack_w2_image(const bf16* w2_packed, uint8_t* img, cudaStream_t st);
+// band (optional, exact row sharding of one frame): h1 has `halo` valid rows above/below, statistics use frame row yg0 + y of Hf rows
+struct FfnBand { int halo, yg0, Hf; };
 int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const uint8_t* w2_img, const float* b2, const float* gamma,
-                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, bf16* shadow, int num_sms, cudaStream_t st);
+                    const float* beta, float* x, int B, int H, int W, const FfnStats* stats, bf16* shadow, int num_sms, cudaStream_t st,
+                    const FfnBand* band = nullptr);
 // proj_fc1.cu: proj + norm1 + residual chained with fc1 + GELU (the bf16 copy of the stream stays in shared memory); tm_wp = packed proj
 // weights (box {64, 192}), w1 = packed fc1 weights bf16 [384][192], res / xout fp32 [N][180], h1 bf16 [N][384]
 int launch_proj_fc1(const bf16* outsc, const CUtensorMap& tm_wp, const float* bp, const float* gamma, const float* beta, const float* res,
@@ -70,6 +74,9 @@ int casa_bfrag_words();
 int launch_pack_casa_bfrag(CasaW w, uint32_t* img, cudaStream_t st);
 struct PadGeom {
   int B, H, W, Hp, Wp;     // real and reflect-padded sizes
+  // band mode (one frame sharded by rows, zero-initialised = off): this band starts at frame row y0 of a frame with Hf rows padded to
+  // Hpf; `top` / `bot` say that the per-pixel statistic maps carry one valid halo row of the neighbour band above / below
+  int y0, Hf, Hpf, top, bot;
 };
 // per padded pixel channel mean / max + deterministic per-image per-channel (sum, max) partials
 int launch_sca_stats(const float* x, PadGeom g, float* cavg, float* cmax, float* part_sum, float* part_max, int nparts, cudaStream_t st);
@@ -124,13 +131,17 @@ struct UaW {
   const float* c3_w; const float* c3_b;
 };
 // stats of X = a (+ b if b != nullptr) over channels / rows / columns
+// Hf (band mode) = rows of the whole frame: havg holds sum / Hf of the band's rows, so that an all-reduce SUM over the bands is the mean
 int launch_ua_stats(const float* a, const float* b, int B, int H, int W,
                     float* cavg, float* cmax,        // [B,H,W]
                     float* havg, float* hmax,        // [B,C,W]  (reduced over H)
-                    float* wavg, float* wmax,        // [B,C,H]  (reduced over W)
-                    cudaStream_t st);
+                    float* wavg, float* wmax,        // [B,H,C]  (reduced over W; row-major in y so that a band's halo rows are contiguous)
+                    cudaStream_t st, int Hf = 0);
+// top / bot (band mode): cavg, cmax, wavg, wmax carry one valid halo row above / below
 int launch_ua_small_convs(int B, int H, int W, UaW w, const float* cavg, const float* cmax, const float* havg, const float* hmax,
-                          const float* wavg, const float* wmax, float* c_att, float* h_att, float* w_att, cudaStream_t st);
+                          const float* wavg, const float* wmax, float* c_att, float* h_att, float* w_att, cudaStream_t st, int top = 0, int bot = 0);
+// out_sum / out_max [180] = sum / max over the nparts partials of one image (band mode: the vectors that are all-reduced)
+int launch_reduce_parts(const float* part_sum, const float* part_max, int nparts, float* out_sum, float* out_max, cudaStream_t st);
 // S[n, c] = c_att[y,x] + w_att[c,y] + h_att[c,x]  -> bf16 [N,192]
 int launch_ua_build(int B, int H, int W, const float* c_att, const float* h_att, const float* w_att, bf16* s, cudaStream_t st);
 // out = first*sigmoid(a1*sigmoid(a2)) + second*sigmoid(a3*(1-sigmoid(a2)))  -> bf16 [N,192] (+ fp32 tap)

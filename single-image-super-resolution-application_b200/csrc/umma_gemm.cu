@@ -87,7 +87,7 @@ umma_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (p.conv) {
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma_load_4d(sa, &tmap_a, full_bar(stage), cb * 64, x0 + dx, y0 + dy, b);
+            tma_load_4d(sa, &tmap_a, full_bar(stage), cb * 64, x0 + dx, y0 + dy + p.a_y_off, b);
           } else {
             tma_load_2d(sa, &tmap_a, full_bar(stage), kb * 64, m_tile * 128);
           }

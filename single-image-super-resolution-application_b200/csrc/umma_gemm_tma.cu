@@ -172,7 +172,7 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
           mbar_expect_tx(full_bar(stage), Cfg::kStageBytes);
           if (p.conv) {
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-            tma_load_4d(sa, &tmap_a, full_bar(stage), cb * 64, t.x0 + tap % 3 - 1, t.y0 + tap / 3 - 1, t.b);
+            tma_load_4d(sa, &tmap_a, full_bar(stage), cb * 64, t.x0 + tap % 3 - 1, t.y0 + tap / 3 - 1 + p.a_y_off, t.b);
           } else {
             tma_load_2d(sa, &tmap_a, full_bar(stage), kb * 64, t.m_tile * 128);
           }

@@ -8,7 +8,7 @@ n = sys.argv[1]
 try:
     d = json.loads(open(f"gpurun_out/bench_n{n}.log").read().strip().split("\n")[-1])
     print("N", d["n_gpus"], "value", d["value"], "ms", d["ms_per_step"], "collective:", d["config"]["collective"][:60])
-    print("cfg4", d.get("cfg4")); print("cfg3", d.get("cfg3"))
+    print("cfg4", d.get("cfg4")); print("cfg3", d.get("cfg3")); print("cfg3_exact", d.get("cfg3_exact"))
 except Exception as e:
     print("parse failed", e)
 PY
