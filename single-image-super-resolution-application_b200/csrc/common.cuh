@@ -68,7 +68,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // is the binding resource of the FFN kernels, the MUFU pipe is otherwise idle).  Saturates exactly: 2^z -> inf gives 0, 2^z -> 0 gives x.
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ float2 gelu2(float2 x) {
+__device__ __forceinline__ float2 gelu2_exact(float2 x) {
   float2 s = __fmul2_rn(x, x);
   s.x = fminf(s.x, 81.f); s.y = fminf(s.y, 81.f);          // the quintic turns over at |x| ~ 11.4; beyond 9 the logistic is saturated anyway
   float2 p = __ffma2_rn(s, make_float2(9.481962249e-04f, 9.481962249e-04f), make_float2(-1.064097551e-01f, -1.064097551e-01f));
@@ -77,6 +77,26 @@ __device__ __forceinline__ float2 gelu2(float2 x) {
   const float2 e = __fadd2_rn(make_float2(ex2_approx(z.x), ex2_approx(z.y)), make_float2(1.f, 1.f));
   return __fmul2_rn(x, make_float2(rcp_approx(e.x), rcp_approx(e.y)));
 }
+// The same logistic written with ONE MUFU op per value: 1 / (1 + 2^z) = (1 + tanh(-z ln2 / 2)) / 2, so x Phi(x) = hx + hx tanh(w) with hx = x / 2,
+// w = x (a' + b' s + c' s^2) (the quintic scaled by ln2 / 2).  5 packed FMA-pipe instructions + 2 FMNMX + 2 MUFU per pair instead of 6 + 2 + 4: the fc1
+// epilogue was MUFU-bound (67 % of the pipe, profiles/r1i).  tanh.approx.f32 has a relative error of 2^-11, i.e. an ABSOLUTE error of up to
+// 2.4e-4 |x| on the result (where x < 0 the result itself is smaller than that) -- an eighth of the bf16 rounding step of a stored value of
+// magnitude |x|, which is what the consumers of h1 / h2 see anyway.
+__device__ __forceinline__ float tanh_approx(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float2 gelu2_tanh(float2 x) {
+  float2 s = __fmul2_rn(x, x);
+  s.x = fminf(s.x, 81.f); s.y = fminf(s.y, 81.f);
+  float2 p = __ffma2_rn(s, make_float2(-3.286197700e-04f, -3.286197700e-04f), make_float2(3.687881087e-02f, 3.687881087e-02f));
+  p = __ffma2_rn(p, s, make_float2(7.976246503e-01f, 7.976246503e-01f));
+  const float2 w = __fmul2_rn(p, x);
+  const float2 hx = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(hx, make_float2(tanh_approx(w.x), tanh_approx(w.y)), hx);
+}
+#ifdef HITSIR_GELU_EXACT
+__device__ __forceinline__ float2 gelu2(float2 x) { return gelu2_exact(x); }
+#else
+__device__ __forceinline__ float2 gelu2(float2 x) { return gelu2_tanh(x); }
+#endif
 
 __device__ __forceinline__ float lrelu(float x, float slope) { return x > 0.f ? x : x * slope; }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
@@ -143,6 +163,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra LAB_WAIT;\n\t"
       "DONE:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// Same wait for the single-role warps (producer, MMA issuer, DMA, statistics) that share a scheduler with four compute warps: the plain
+// loop above re-issues try_wait every ~7 cycles (ncu: a third of all instructions of ffn_tail were SYNCS / BRA / YIELD of role warps,
+// 43 % of the issue slots of the sub-partition that hosts the statistics warp).  With a suspend-time hint the hardware parks the
+// thread until the phase completes (or the hint expires) instead of returning at once.
+__device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity, uint32_t hint_ns = 1000u) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity), "r"(hint_ns) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
