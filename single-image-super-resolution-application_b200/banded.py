@@ -225,21 +225,37 @@ class LocalBandedSR:
 class BandedSR:
     """One band per rank of `group` (default: the world).  Construct it collectively on every rank; `forward(x)` takes the SAME whole
     frame on every rank (1, C, H, W) and returns the whole SR frame on `dst_rank` (None elsewhere; every rank when dst_rank is None).
-    The group must have exactly len(band_plan(H, world)) ranks (a 1080-row frame has at most 6 bands): build it on a sub-group."""
+    The group must have exactly len(band_plan(H, world)) ranks (a 1080-row frame has at most 6 bands): build it on a sub-group.
 
-    def __init__(self, model, group=None):
+    `graphed=True` captures the band forward of a frame shape -- this rank's ~260 kernel launches TOGETHER with its ~175 exchanges
+    (barrier kernels of the symmetric-memory handle, peer copies, NCCL all-reduces) -- into one CUDA graph and replays it: the exchange
+    callbacks are Python, and at 6 bands of a 1080p frame a band's kernels last ~100 us each, so the eager path is bound by the host."""
+
+    def __init__(self, model, group=None, graphed: bool = False):
         import torch.distributed as dist
         self.model = model
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
+        self.graphed = graphed
         self._ws = None
         self._key = None
+        self._graph = None
+        self._gkey = None
+        self.captures = 0
+
+    def close(self):
+        """Drop the captured graph.  Call it (or delete the object) BEFORE `dist.destroy_process_group()`: tearing down the NCCL
+        communicator while a CUDA graph that holds its collectives is alive blocks forever (measured: PyTorch 2.11 / NCCL 2.28)."""
+        self._graph = None
+        self._gkey = None
 
     def _workspace(self, device, layout_h, W):
         import torch.distributed._symmetric_memory as symm_mem
         key = (layout_h, W)
         if self._key != key:
+            self._graph = None                                                # a captured graph points into the old workspace
+            self._gkey = None
             nbytes = _workspace_bytes(self.model, device, layout_h, W)
             self._ws = symm_mem.empty((nbytes,), dtype=torch.uint8, device=device)
             self._hdl = symm_mem.rendezvous(self._ws, self.group)
@@ -247,27 +263,18 @@ class BandedSR:
             self._key = key
         return self._ws
 
-    def forward(self, x: torch.Tensor, dst_rank: Optional[int] = 0) -> Optional[torch.Tensor]:
+    def _run_band(self, x, y_band, plan, layout_h):
+        """Enqueue this rank's band of the forward (kernels + exchanges) on the current stream."""
         import torch.distributed as dist
         model = self.model
         device = x.device
-        x = x.detach().float().contiguous()
         _, C, Hf, W = x.shape
-        s = model.out_scale
-        plan = band_plan(Hf, self.world)
         R = len(plan)
-        if R != self.world:          # raised on EVERY rank before anything is enqueued: the exchanges are collective over the group
-            raise RuntimeError(f"BandedSR: a frame of {Hf} rows has {R} band(s) of 192-row units but the group has {self.world} ranks; "
-                               f"build it on a sub-group of {R} rank(s) (band_plan)")
-        layout_h = max(r for _, r in plan)
-        cur = torch.cuda.current_stream(device)
-        with torch.cuda.device(device):
-            h = model._handle(device)
-            model._sync_weights(h, device, cur.cuda_stream)
-        ws = self._workspace(device, layout_h, W)
+        ws = self._ws
         base = (ws.data_ptr() + 255) // 256 * 256 - ws.data_ptr()           # identical on every rank (symmetric allocations are equally aligned)
         me = self.rank
         hdl, peers = self._hdl, self._peers
+        cur = torch.cuda.current_stream(device)
 
         def halo(_ctx, off, row_bytes, rows, halo_rows, _stream):
             try:
@@ -297,7 +304,6 @@ class BandedSR:
 
         self._err = None
         row0, rows = plan[me]
-        y_band = torch.empty((1, C, s * rows, s * W), dtype=torch.float32, device=device)
         hcb, acb = _capi.HALO_FN(halo), _capi.ALLREDUCE_FN(allreduce)
         band = _band_struct(Hf, row0, layout_h, me > 0, me < R - 1, hcb, acb)
         try:
@@ -306,6 +312,56 @@ class BandedSR:
             if self._err is not None:
                 raise self._err
             raise
+
+    def _capture(self, x, plan, layout_h, y_shape):
+        device = x.device
+        self._graph = None
+        self._gx = x.clone()
+        self._gy = torch.empty(y_shape, dtype=torch.float32, device=device)
+        cur = torch.cuda.current_stream(device)
+        side = torch.cuda.Stream(device=device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():
+            self._run_band(self._gx, self._gy, plan, layout_h)               # eager warm-up: kernels opt in to their shared memory, NCCL connects
+            side.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=side, capture_error_mode="thread_local"):
+                self._run_band(self._gx, self._gy, plan, layout_h)
+        cur.wait_stream(side)
+        self._graph = graph
+        self.captures += 1
+
+    def forward(self, x: torch.Tensor, dst_rank: Optional[int] = 0) -> Optional[torch.Tensor]:
+        import torch.distributed as dist
+        model = self.model
+        device = x.device
+        x = x.detach().float().contiguous()
+        _, C, Hf, W = x.shape
+        s = model.out_scale
+        plan = band_plan(Hf, self.world)
+        R = len(plan)
+        if R != self.world:          # raised on EVERY rank before anything is enqueued: the exchanges are collective over the group
+            raise RuntimeError(f"BandedSR: a frame of {Hf} rows has {R} band(s) of 192-row units but the group has {self.world} ranks; "
+                               f"build it on a sub-group of {R} rank(s) (band_plan)")
+        layout_h = max(r for _, r in plan)
+        cur = torch.cuda.current_stream(device)
+        with torch.cuda.device(device):
+            h = model._handle(device)
+            model._sync_weights(h, device, cur.cuda_stream)
+        self._workspace(device, layout_h, W)
+        me = self.rank
+        y_shape = (1, C, s * plan[me][1], s * W)
+        if self.graphed:
+            gkey = (tuple(x.shape), model._weights_key(), model.native_handle(device))
+            if self._graph is None or self._gkey != gkey:                    # same decision on every rank: same frame, same weights
+                self._capture(x, plan, layout_h, y_shape)
+                self._gkey = gkey
+            self._gx.copy_(x, non_blocking=True)
+            self._graph.replay()
+            y_band = self._gy
+        else:
+            y_band = torch.empty(y_shape, dtype=torch.float32, device=device)
+            self._run_band(x, y_band, plan, layout_h)
         # reassemble: bands are row blocks of an NCHW tensor
         pad_rows = s * layout_h
         mine = torch.zeros((1, C, pad_rows, s * W), dtype=torch.float32, device=device)

@@ -196,6 +196,9 @@ def test_band_mode_rejects_misaligned_bands():
 # ---- 2 GPUs: one band per rank, symmetric-memory halo pushes over NVLink + NCCL all-reduces (BandedSR) -----------------------------------
 def _nccl_worker(rank, world, port, out_dir):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import faulthandler
+    import sys
+    faulthandler.dump_traceback_later(150, exit=True, file=sys.stderr)      # a hung exchange must not hold the GPU box: dump the stacks and exit
     torch.cuda.set_device(rank)
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", device_id=dev)
@@ -219,7 +222,16 @@ def _nccl_worker(rank, world, port, out_dir):
             # NCCL's and the local harness's two-operand sums commute, so the two banded runs see identical statistics
             assert err_local == 0.0, err_local
             assert err_full < 6e-2 / 4, err_full
+            # the same band forward captured with its exchanges into one CUDA graph and replayed (twice: the barriers hold no state)
+            graphed = BandedSR(model, graphed=True)
+            with torch.no_grad():
+                g1 = graphed.forward(x, dst_rank=None).clone()
+                g2 = graphed.forward(x, dst_rank=None)
+            torch.cuda.synchronize()
+            assert graphed.captures == 1 and torch.equal(g1, y) and torch.equal(g2, y)
+            graphed.close()                                   # before destroy_process_group: a live graph with NCCL nodes blocks the teardown
         open(os.path.join(out_dir, f"ok_{rank}"), "w").close()
+        faulthandler.cancel_dump_traceback_later()
     finally:
         dist.destroy_process_group()
 
