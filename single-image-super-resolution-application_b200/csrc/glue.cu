@@ -506,12 +506,17 @@ __global__ void __launch_bounds__(96, 10) qkv_casa_kernel(const float* __restric
 // warp-level bf16 MMAs (m16n8k16, fp32 accumulate) with a three-term split so that nothing is lost to bf16:
 //     k  0.. 8: a_hi[tap] * W_hi[tap]      k  9..17: a_lo[tap] * W_hi[tap]      k 18..26: a_hi[tap] * W_lo[tap]
 //     k 27, 28: 1 * b_hi, 1 * b_lo         k 29..31: 0                          (x = x_hi + x_lo, both bf16: ~16 mantissa bits)
-// CTA = (image, padded row), 4 warps, 5 CTAs per SM; per run of 32 padded pixels: the token rows are staged with cp.async (16-byte chunks through the
-// reflect map), every warp owns 6 n-tiles (48 head-padded positions) whose B fragments stay in registers for the whole row, the A
+// CTA = (image, padded row), 4 warps, 5 CTAs per SM (96 registers); per run of 32 padded pixels: the token rows are staged by ONE bulk copy (the
+// pixels of a run are contiguous in global memory; only the reflected tail of a padded row goes pixel by pixel) that completes on an
+// mbarrier -- per-thread 16-byte cp.async chunks (45 per row) ran at 4.0 TB/s, the bulk copy at 4.7 --, every warp owns 6 n-tiles
+// (48 head-padded positions) whose B fragments stay in registers for the whole row, the A
 // rows [32 px][32 k] of both statistic maps are built once per run in shared memory, and the gated bf16 tokens leave through a
 // padded shared tile as whole 16-byte chunks.  What is left per output: 2 LeakyReLU, 2 FMA, the token read and the bf16 pack.
+#ifndef QKV_MIN_CTAS
+#define QKV_MIN_CTAS 5                           // 96 registers, no spills: shared memory (43 KB per CTA) then allows 5 CTAs per SM instead of 3 at 140 registers
+#endif
 constexpr int kMmaRun = 32;
-constexpr int kMmaXS = 184;                      // staged token row: 180 fp32 + 4 (row = 736 B, a multiple of 16)
+constexpr int kMmaXS = 180;                      // staged token rows keep their global pitch (720 B): a run of pixels is ONE bulk copy
 constexpr int kMmaOS = 100;                      // output row: 96 words + 4 (rows of a quad-store land on distinct banks)
 constexpr int kMmaAS = 20;                       // A row: 16 words + 4
 constexpr int kMmaSmem = kMmaRun * kMmaXS * 4 + kMmaRun * kMmaOS * 4 + 2 * kMmaRun * kMmaAS * 4 + 2 * kCp * 4 + 2 * 3 * (kMmaRun + 2) * 4;
@@ -548,7 +553,7 @@ __global__ void casa_bfrag_kernel(CasaW w, uint32_t* __restrict__ img) {
   img[idx] = (uint32_t)out[0] | ((uint32_t)out[1] << 16);
 }
 
-__global__ void __launch_bounds__(128) qkv_casa_mma_kernel(const float* __restrict__ x, PadGeom g, const float* __restrict__ cavg,
+__global__ void __launch_bounds__(128, QKV_MIN_CTAS) qkv_casa_mma_kernel(const float* __restrict__ x, PadGeom g, const float* __restrict__ cavg,
                                                            const float* __restrict__ cmax, const float* __restrict__ s1, const float* __restrict__ s2,
                                                            const uint32_t* __restrict__ bfrag, bf16* __restrict__ t) {
   extern __shared__ __align__(16) uint8_t smem_casa[];
@@ -564,16 +569,24 @@ __global__ void __launch_bounds__(128) qkv_casa_mma_kernel(const float* __restri
   const float* ca = cavg + (long long)b * g.H * g.W;
   const float* cm = cmax + (long long)b * g.H * g.W;
   const uint32_t xs_addr = (uint32_t)__cvta_generic_to_shared(xs);
+  __shared__ __align__(8) uint64_t xbar_storage;
+  const uint32_t xbar = (uint32_t)__cvta_generic_to_shared(&xbar_storage);
+  if (tid == 0) { mbar_init(xbar, 1); fence_barrier_init(); }
+  __syncthreads();
+  uint32_t xphase = 0;
+  // one elected thread: the pixels of a run that lie inside the row are contiguous in global memory (one bulk copy), the reflected tail of
+  // the last run is fetched pixel by pixel (720-byte bulk copies); everything completes on one mbarrier
   auto stage_x = [&](int xs0) {
+    if (tid != 0) return;
     const int n = min(kMmaRun, g.Wp - xs0);
-    for (int px = warp; px < n; px += 4) {                 // a token row is 45 chunks of 16 bytes: lanes 0..31, then lanes 0..12
-      const float* src = xrow + (long long)reflect_src(xs0 + px, g.W) * kC + lane * 4;
-      const uint32_t dst = xs_addr + (uint32_t)(px * kMmaXS + lane * 4) * 4u;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-      if (lane < 13) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 512u), "l"(src + 128) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int nin = max(0, min(n, g.W - xs0));           // pixels of the run inside [0, W)
+    fence_proxy_async_smem();                            // the previous run's generic-proxy reads of the buffer precede these async-proxy writes
+    mbar_expect_tx(xbar, (uint32_t)(n * kC * 4));
+    if (nin > 0) bulk_load(xs_addr, xrow + (long long)xs0 * kC, (uint32_t)(nin * kC * 4), xbar);
+    for (int px = nin; px < n; ++px)
+      bulk_load(xs_addr + (uint32_t)(px * kC * 4), xrow + (long long)reflect_src(xs0 + px, g.W) * kC, (uint32_t)(kC * 4), xbar);
   };
+  auto stage_wait = [&]() { mbar_wait(xbar, xphase); xphase ^= 1u; };
   float gv[3];                                             // 0.5 * channel gates of this image: fetched first, stored after the B fragments
 #pragma unroll
   for (int e = 0; e < 3; ++e) {
@@ -629,7 +642,7 @@ __global__ void __launch_bounds__(128) qkv_casa_mma_kernel(const float* __restri
                              (uint32_t)row[8 * c4 + 4] | ((uint32_t)row[8 * c4 + 5] << 16), (uint32_t)row[8 * c4 + 6] | ((uint32_t)row[8 * c4 + 7] << 16));
       }
     }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    stage_wait();
     __syncthreads();                                       // A rows, gates and this run's token rows are visible
 #pragma unroll 1
     for (int pt = 0; pt < kMmaRun / 16; ++pt) {
@@ -806,19 +819,30 @@ __global__ void ua_build_kernel(int B, int H, int W, const float* __restrict__ c
   }
 }
 
-__global__ void fusion_combine_kernel(const float* __restrict__ first, const float* __restrict__ second, const float* __restrict__ a1,
-                                      const float* __restrict__ a2, const float* __restrict__ a3, bf16* __restrict__ out, float* __restrict__ of, long long N) {
-  const long long total = N * kCp;
+// thread = (pixel, 4 consecutive channels): 180 = 45 chunks of 4, chunks 45..47 are the zero pad of the bf16 operand row.  sigmoid(x) =
+// 0.5 + 0.5 tanh(x / 2) on one MUFU op (tanh.approx.f32 is within 2e-6 of tanh, tools/ubench/tanh_probe.cu); the element-per-thread
+// version with three exp + divide sigmoids and a 64-bit division per element was instruction-bound at 3.2 TB/s.
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__global__ void __launch_bounds__(256) fusion_combine_kernel(const float* __restrict__ first, const float* __restrict__ second, const float* __restrict__ a1,
+                                                             const float* __restrict__ a2, const float* __restrict__ a3, bf16* __restrict__ out,
+                                                             float* __restrict__ of, long long N) {
+  constexpr int kChunks = kCp / 4;   // 48
+  const long long total = N * kChunks;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const long long r = idx / kCp; const int c = (int)(idx - r * kCp);
-    float v = 0.f;
-    if (c < kC) {
-      const long long i = r * kC + c;
-      const float att = sigmoidf_(a2[i]);                                       // (:152)
-      v = first[i] * sigmoidf_(a1[i] * att) + second[i] * sigmoidf_(a3[i] * (1.f - att));   // (:155-162)
-      if (of != nullptr) of[i] = v;
+    const long long r = idx / kChunks; const int c4 = (int)(idx - r * kChunks);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c4 < kC / 4) {
+      const long long i = r * kC + 4 * c4;
+      const float4 f = *reinterpret_cast<const float4*>(first + i), sc = *reinterpret_cast<const float4*>(second + i);
+      const float4 x1 = *reinterpret_cast<const float4*>(a1 + i), x2 = *reinterpret_cast<const float4*>(a2 + i), x3 = *reinterpret_cast<const float4*>(a3 + i);
+      const float t0 = sigmoid_fast(x2.x), t1 = sigmoid_fast(x2.y), t2 = sigmoid_fast(x2.z), t3 = sigmoid_fast(x2.w);                  // (:152)
+      v.x = f.x * sigmoid_fast(x1.x * t0) + sc.x * sigmoid_fast(x3.x * (1.f - t0));                                                  // (:155-162)
+      v.y = f.y * sigmoid_fast(x1.y * t1) + sc.y * sigmoid_fast(x3.y * (1.f - t1));
+      v.z = f.z * sigmoid_fast(x1.z * t2) + sc.z * sigmoid_fast(x3.z * (1.f - t2));
+      v.w = f.w * sigmoid_fast(x1.w * t3) + sc.w * sigmoid_fast(x3.w * (1.f - t3));
+      if (of != nullptr) *reinterpret_cast<float4*>(of + i) = v;
     }
-    out[idx] = __float2bfloat16(v);
+    *reinterpret_cast<uint2*>(out + r * kCp + 4 * c4) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
   }
 }
 
@@ -988,7 +1012,7 @@ int launch_ua_build(int B, int H, int W, const float* c_att, const float* h_att,
 }
 int launch_fusion_combine(const float* first, const float* second, const float* a1, const float* a2, const float* a3, bf16* out, float* of, long long N,
                           cudaStream_t st) {
-  fusion_combine_kernel<<<grid_for(N * kCp, 256), 256, 0, st>>>(first, second, a1, a2, a3, out, of, N);
+  fusion_combine_kernel<<<grid_for(N * (kCp / 4), 256), 256, 0, st>>>(first, second, a1, a2, a3, out, of, N);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }
