@@ -195,6 +195,186 @@ conv3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// x2 nearest upsampling + 3x3 conv 64 -> 64 + bias + LeakyReLU without the upsampled map (conv_up1 / conv_up2, :1331-1332).
+// Output phase (a, b) = (Y & 1, X & 1) of the HR map is a 2x2 conv of the LR map with the phase filters of pack_subpixel_kernel:
+// 16 instead of 36 tap-MMAs per HR pixel quad, the LR map is read instead of a 4x larger replicated one, and the upsample2 pass
+// (write + read of the replicated map) is gone.  Per 8 x 16 LR tile the three kx boxes of the plain kernel feed four accumulators
+// [128 x 64] (one per phase, 256 TMEM columns, double-buffered = all 512); box kx serves the phases with dx = kx - 1 in {b - 1, b}.
+// The four results leave through four tensor maps over the HR map (pixel stride 2, row stride 2, base offset (a, b)), so the TMA
+// store does the interleaving and clips at the LR image size.
+constexpr int kUpAStages = 3;
+constexpr int kUpNBox = 2;
+struct UpCfg {
+  static constexpr int kBBytes = 16 * 64 * 128;                       // resident phase filters: 4 phases x 4 taps x [64 x 64]
+  static constexpr int kOffA = kBBytes;
+  static constexpr int kOffBox = kOffA + kUpAStages * kATile;
+  static constexpr int kOffBias = kOffBox + kUpNBox * kBoxBytes;
+  static constexpr int kOffBars = kOffBias + 64 * 4;
+  static constexpr int kSmemBytes = kOffBars + 32 * 8 + 16 + 1024;
+};
+static_assert(UpCfg::kSmemBytes <= 232448 && UpCfg::kOffA % 1024 == 0 && UpCfg::kOffBox % 1024 == 0, "smem budget / alignment");
+
+__global__ void __launch_bounds__(384, 1)
+conv3_c64_up_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o0,
+                    const __grid_constant__ CUtensorMap tmap_o1, const __grid_constant__ CUtensorMap tmap_o2, const __grid_constant__ CUtensorMap tmap_o3,
+                    const GemmParams p) {
+  using C = UpCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sb - smem_u32(smem_raw));
+  float* s_bias = reinterpret_cast<float*>(sp + C::kOffBias);
+  const uint32_t bar0 = sb + C::kOffBars;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kUpAStages + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kUpAStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kUpAStages + 2 + s); };
+  auto box_free = [&](int s) { return bar0 + 8u * (2 * kUpAStages + 4 + s); };
+  auto box_ready = [&](int s) { return bar0 + 8u * (2 * kUpAStages + 4 + kUpNBox + s); };
+  const uint32_t b_full = bar0 + 8u * (2 * kUpAStages + 4 + 2 * kUpNBox);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sp + C::kOffBars + 32 * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.m_tiles;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b);
+    tma_prefetch_desc(&tmap_o0); tma_prefetch_desc(&tmap_o1); tma_prefetch_desc(&tmap_o2); tma_prefetch_desc(&tmap_o3);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kUpAStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+    for (int s = 0; s < kUpNBox; ++s) { mbar_init(box_free(s), 1); mbar_init(box_ready(s), 8); }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), 512); tmem_relinquish(); }
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) s_bias[i] = p.bias[i];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_xyb = [&](int t, int* x0, int* y0, int* b) {
+    const int tx = t % p.tiles_x; const int t2 = t / p.tiles_x;
+    *x0 = tx * 16; *y0 = (t2 % p.tiles_y) * 8; *b = t2 / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== producer: phase filters once, then one LR halo box per (tile, kx) =====================
+      mbar_expect_tx(b_full, (uint32_t)C::kBBytes);
+      for (int tap = 0; tap < 16; ++tap) tma_load_2d(sb + tap * 64 * 128, &tmap_b, b_full, tap * 64, 0);
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        for (int kx = 0; kx < 3; ++kx, ++cnt) {
+          const int s = (int)(cnt % kUpAStages);
+          mbar_wait(empty_bar(s), ((cnt / kUpAStages) & 1u) ^ 1u);
+          mbar_expect_tx(full_bar(s), kATile);
+          tma_load_4d(sb + C::kOffA + s * kATile, &tmap_a, full_bar(s), 0, x0 + kx - 1, y0 - 1 + p.a_y_off, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer: LR offset (dy, dx) = (ky - 1, kx - 1) feeds phase (a, b) iff ky - a, kx - b in {0, 1} =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 64);
+      mbar_wait(b_full, 0u);
+      uint32_t cnt = 0;
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        mbar_wait(tempty_bar(as), (((uint32_t)(it >> 1)) & 1u) ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx, ++cnt) {
+          const int s = (int)(cnt % kUpAStages);
+          mbar_wait(full_bar(s), (cnt / kUpAStages) & 1u);
+          tc_fence_after();
+          const uint32_t sa = sb + C::kOffA + s * kATile;
+#pragma unroll
+          for (int ky = 0; ky < 3; ++ky) {
+            const uint64_t adesc = umma_desc_sw128(sa + ky * 2048);
+#pragma unroll
+            for (int a = 0; a < 2; ++a) {
+              const int dyi = ky - a;
+              if (dyi < 0 || dyi > 1) continue;
+#pragma unroll
+              for (int b = 0; b < 2; ++b) {
+                const int dxi = kx - b;
+                if (dxi < 0 || dxi > 1) continue;
+                const int ph = 2 * a + b;
+                const uint64_t bdesc = umma_desc_sw128(sb + ((ph * 4 + dyi * 2 + dxi) * 64) * 128);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)      // (dyi, dxi) = (0, 0) is the first tap of every phase in this loop order
+                  umma_bf16(d_tmem + (uint32_t)(ph * 64), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (dyi | dxi | k) != 0 ? 1u : 0u);
+              }
+            }
+          }
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else if (warp == 3) {
+    if (lane == 0) {
+      // ===================== TMA store: box u = (tile, phase) through the phase's strided view of the HR map =====================
+      uint32_t u = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        for (int ph = 0; ph < 4; ++ph, ++u) {
+          const int s = (int)(u % kUpNBox);
+          mbar_wait(box_ready(s), (u / kUpNBox) & 1u);
+          const CUtensorMap* tm = ph == 0 ? &tmap_o0 : ph == 1 ? &tmap_o1 : ph == 2 ? &tmap_o2 : &tmap_o3;
+          tma_store_4d(tm, sb + C::kOffBox + s * kBoxBytes, 0, x0, y0, b);
+          tma_commit();
+          tma_wait_read1();                                  // groups retire in order: the previous box is free again
+          if (u >= 1) mbar_arrive(box_free((int)((u - 1) % kUpNBox)));
+        }
+      }
+      tma_wait_all0();
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue: 8 warps, two per TMEM lane quarter; four phase boxes per tile =====================
+    const int q = warp & 3, hs = (warp - 4) >> 2;
+    const int r = q * 32 + lane;
+    int it = 0;
+    uint32_t u = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+      const int as = it & 1;
+      mbar_wait(tfull_bar(as), ((uint32_t)(it >> 1)) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 256);
+#pragma unroll 1
+      for (int ph = 0; ph < 4; ++ph, ++u) {
+        float v[32];
+        tmem_ld32(tacc + 64 * ph + 32 * hs, v);
+        if (ph == 3) { tc_fence_before(); mbar_arrive_warp(tempty_bar(as)); }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const float x = v[i] + s_bias[32 * hs + i]; v[i] = p.act == ACT_LRELU ? lrelu(x, p.slope) : x; }
+        const int s = (int)(u % kUpNBox);
+        if (u >= (uint32_t)kUpNBox) mbar_wait(box_free(s), ((u / kUpNBox) - 1u) & 1u);
+        uint8_t* row = sp + C::kOffBox + s * kBoxBytes + r * 128;
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) {
+          const uint4 o = make_uint4(pack_bf16x2(v[8 * ch], v[8 * ch + 1]), pack_bf16x2(v[8 * ch + 2], v[8 * ch + 3]),
+                                     pack_bf16x2(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16x2(v[8 * ch + 6], v[8 * ch + 7]));
+          *reinterpret_cast<uint4*>(row + (((uint32_t)(4 * hs + ch) ^ (uint32_t)(r & 7)) << 4)) = o;
+        }
+        fence_proxy_async_smem();
+        mbar_arrive_warp(box_ready(s));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 template <int BN>
 int launch_bn(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, int num_sms, cudaStream_t st) {
   using C = Cfg<BN>;
@@ -222,6 +402,23 @@ int launch_conv3_c64(int BN, const GemmParams& p, const bf16* A, const CUtensorM
   if (BN == 16) return launch_bn<16>(p, ta, tb, to, num_sms, st);
   set_error("launch_conv3_c64: unsupported N tile %d", BN);
   return 1;
+}
+
+// A: NHWC bf16 [B,H,W,64] (the LR map; band mode: a_y_off valid halo rows above and below); tb: phase filters [64][1024] with a {64, 64} box;
+// out_bf16: [B,2H,2W,64]
+int launch_conv3_c64_up(const GemmParams& p, const bf16* A, const CUtensorMap& tb, int num_sms, cudaStream_t st) {
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(conv3_c64_up_kernel, UpCfg::kSmemBytes, &configured)) return 1;
+  CUtensorMap ta, to[4];
+  if (make_tmap_nhwc(&ta, A - (size_t)p.a_y_off * p.W * 64, p.B, p.H + 2 * p.a_y_off, p.W, 64, 64, 16, 10)) return 1;
+  const uint64_t pix = 2 * 64 * sizeof(bf16), row = (uint64_t)2 * (2 * p.W) * 64 * sizeof(bf16), img = (uint64_t)(2 * p.H) * (2 * p.W) * 64 * sizeof(bf16);
+  for (int ph = 0; ph < 4; ++ph)
+    if (make_tmap_nhwc_strided(&to[ph], p.out_bf16 + ((size_t)(ph >> 1) * 2 * p.W + (ph & 1)) * 64, p.B, p.H, p.W, 64, pix, row, img, 64, 16, 8)) return 1;
+  const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
+  if (grid <= 0) return 0;
+  conv3_c64_up_kernel<<<grid, 384, UpCfg::kSmemBytes, st>>>(ta, tb, to[0], to[1], to[2], to[3], p);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
 }
 
 }  // namespace hitsir

@@ -111,7 +111,11 @@ struct HitsirHandle {
   float* arena = nullptr;      // device fp32 master copy of every parameter
   size_t arena_floats = 0;
   bool finalized = false;
-  std::vector<void*> owned;    // packed buffers
+  // packed buffers live in a few large chunks (bump-allocated in a fixed order, so a re-pack after a weight update lands every table at the
+  // same address): ~600 cudaMalloc / cudaFree pairs per hitsir_finalize_weights were most of its 60-140 ms
+  std::vector<void*> owned;    // chunks
+  std::vector<size_t> chunk_bytes;
+  size_t chunk_cur = 0, chunk_off = 0;
   // packed weights
   GemmW first, first_last;     // conv_first (im2col GEMM) and its 1x1 conv_last (ms only)
   int first_f = 3, first_kp = 64;
@@ -294,12 +298,21 @@ const float* P(const HitsirHandle* h, const std::string& name) {
   return h->arena + h->params[it->second].offset;
 }
 
+constexpr size_t kPackChunkBytes = (size_t)64 << 20;
 template <class T>
 int dev_alloc(HitsirHandle* h, T** p, size_t count) {
-  void* q = nullptr;
-  HITSIR_CHECK(cudaMalloc(&q, count * sizeof(T)));
-  h->owned.push_back(q);
-  *p = reinterpret_cast<T*>(q);
+  const size_t bytes = (count * sizeof(T) + 1023) & ~(size_t)1023;      // 1024: swizzled operand images are bulk-copied to 1024-byte aligned smem
+  while (h->chunk_cur < h->owned.size() && h->chunk_off + bytes > h->chunk_bytes[h->chunk_cur]) { ++h->chunk_cur; h->chunk_off = 0; }
+  if (h->chunk_cur == h->owned.size()) {
+    const size_t cb = bytes > kPackChunkBytes ? bytes : kPackChunkBytes;
+    void* q = nullptr;
+    HITSIR_CHECK(cudaMalloc(&q, cb));
+    h->owned.push_back(q);
+    h->chunk_bytes.push_back(cb);
+    h->chunk_off = 0;
+  }
+  *p = reinterpret_cast<T*>(static_cast<uint8_t*>(h->owned[h->chunk_cur]) + h->chunk_off);
+  h->chunk_off += bytes;
   return 0;
 }
 
@@ -326,15 +339,30 @@ int make_gemm_w(HitsirHandle* h, GemmW* g, const std::string& prefix, int Co, in
   return make_tmap_2d(&g->tm, g->w, (uint64_t)g->K, (uint64_t)Npad, (uint64_t)g->K * 2, 64, (uint32_t)BN);
 }
 
+// conv_up1 / conv_up2 act on a x2 nearest-upsampled map: packed as the four 2x2 phase filters of the equivalent sub-pixel conv
+int make_subpixel_w(HitsirHandle* h, GemmW* g, const std::string& prefix, cudaStream_t st) {
+  g->BN = 64; g->Npad = 64; g->K = 16 * 64;
+  if (dev_alloc(h, &g->w, (size_t)64 * g->K) || dev_alloc(h, &g->b, 64)) return 1;
+  const float* w = P(h, prefix + ".weight");
+  const float* b = P(h, prefix + ".bias");
+  if (!w || !b) { set_error("missing parameter %s", prefix.c_str()); return 1; }
+  if (launch_pack_subpixel(w, b, g->w, g->b, st)) return 1;
+  return make_tmap_2d(&g->tm, g->w, (uint64_t)g->K, 64, (uint64_t)g->K * 2, 64, 64);
+}
+
 void free_owned(HitsirHandle* h) {
   for (void* p : h->owned) cudaFree(p);
-  h->owned.clear();
+  h->owned.clear(); h->chunk_bytes.clear();
+  h->chunk_cur = 0; h->chunk_off = 0;
 }
 
 int finalize(HitsirHandle* h, cudaStream_t st) {
   for (const ParamSpec& p : h->params)
     if (!p.set) { set_error("parameter '%s' was never provided (hitsir_set_param)", p.name.c_str()); return HITSIR_ERR_WEIGHTS; }
-  free_owned(h);
+  // re-pack in place: the chunks are kept and refilled in the same order.  Work that still reads the old tables (possibly on another
+  // stream) must have finished first -- cudaFree used to imply exactly this device-wide wait
+  if (!h->owned.empty()) HITSIR_CHECK(cudaDeviceSynchronize());
+  h->chunk_cur = 0; h->chunk_off = 0;
   h->finalized = false;
   const HitsirConfig& c = h->cfg;
   const int C = kC, ic = c.in_chans;
@@ -475,8 +503,8 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
       break;
     case HITSIR_UP_NEAREST_CONV:
       if (make_gemm_w(h, &h->conv_before_upsample, "conv_before_upsample.0", kNumFeat, C, 9, st)) return 1;
-      if (make_gemm_w(h, &h->conv_up1, "conv_up1", kNumFeat, kNumFeat, 9, st)) return 1;
-      if (make_gemm_w(h, &h->conv_up2, "conv_up2", kNumFeat, kNumFeat, 9, st)) return 1;
+      if (make_subpixel_w(h, &h->conv_up1, "conv_up1", st)) return 1;
+      if (make_subpixel_w(h, &h->conv_up2, "conv_up2", st)) return 1;
       if (make_gemm_w(h, &h->conv_hr, "conv_hr", kNumFeat, kNumFeat, 9, st)) return 1;
       if (make_gemm_w(h, &h->conv_last, "conv_last", ic, kNumFeat, 9, st)) return 1;
       break;
@@ -586,7 +614,7 @@ int layout_workspace(const HitsirHandle* h, int B, int H, int W, void* base, Wor
   size_t up = 0;
   const int s = c.upscale;
   switch (c.upsampler) {
-    case HITSIR_UP_NEAREST_CONV: up = N * kNumFeat * (size_t)(1 + 4 + 4 + 16 + 16); break;   // U0, U0up, U1, U1up(/U3), U2
+    case HITSIR_UP_NEAREST_CONV: up = N * kNumFeat * (size_t)(1 + 4 + 16 + 16); break;   // U0, U1, U2, U3 (no replicated maps: launch_conv3_c64_up)
     case HITSIR_UP_PIXELSHUFFLE: up = N * kNumFeat * (size_t)(1 + 4 + (s > 2 ? s * s : 0)); break;
     default: up = 0; break;
   }
@@ -755,6 +783,24 @@ int conv3(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, 
     }
   }
   return run_gemm(f, cat, w, p, maps, tma);
+}
+
+// x2 nearest upsampling + 3x3 conv 64 -> 64 (+ LeakyReLU) on the LR map A [B,H,W,64] -> out [B,2H,2W,64] (:1331-1332).  Band mode: the
+// LR rows above / below the band are exchanged (one LR row is what the replicated map's halo row was made of)
+int conv3_up(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, int W, GemmParams& p) {
+  p.conv = 1; p.B = B; p.H = H; p.W = W;
+  if (f.band != nullptr) {
+    RUN(fill_halo(f, const_cast<bf16*>(A), (size_t)W * kNumFeat * sizeof(bf16), H, 1));
+    p.a_y_off = 1;
+  }
+  p.tiles_x = cdiv(W, 16); p.tiles_y = cdiv(H, 8);
+  p.m_tiles = B * p.tiles_x * p.tiles_y;
+  p.cblocks = 1;
+  p.A = A; p.lda = kNumFeat;
+  if (w.K != 16 * kNumFeat) { set_error("conv3_up: packed K %d is not the sub-pixel layout", w.K); return 1; }
+  ProfScope ps(f.h, f.st, cat);
+  f.h->launches++;
+  return launch_conv3_c64_up(p, A, w.tm, f.h->num_sms, f.st);
 }
 
 #define TAP(name, src, is_bf16, ld, rows, cols) do { RUN(do_tap(f, name, src, is_bf16, ld, rows, cols)); if (f.stopped) return 0; } while (0)
@@ -1003,24 +1049,21 @@ int forward_impl(Fwd& f, const float* x, float* y) {
   };
   if (c.upsampler == HITSIR_UP_NEAREST_CONV) {
     bf16* U0 = ws.up + gap;
-    bf16* U0up = U0 + Nl * kNumFeat + gap;
-    bf16* U1 = U0up + 4 * Nl * kNumFeat + gap;
-    bf16* U1up = U1 + 4 * Nl * kNumFeat + gap;
-    bf16* U2 = U1up + 16 * Nl * kNumFeat + gap;
-    bf16* U3 = U1up;
+    bf16* U1 = U0 + Nl * kNumFeat + gap;
+    bf16* U2 = U1 + 4 * Nl * kNumFeat + gap;
+    bf16* U3 = U2 + 16 * Nl * kNumFeat + gap;
     base_params(p, h->conv_before_upsample);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.01f; p.n_real = kNumFeat; p.out_bf16 = U0; p.ldb = kNumFeat;   // nn.LeakyReLU() default slope (:1251)
     RUN(conv3(f, "conv_before_upsample", h->conv_before_upsample, F, B, H, W, kCp, p));
     TAP("conv_before_upsample", U0, 1, kNumFeat, N, kNumFeat);
-    LAUNCH("upsample2", 1, launch_upsample_nearest2(U0, U0up, B, H, W, kNumFeat, f.st));
+    // interpolate(x2, nearest) + conv_up{1,2} (:1331-1332) as sub-pixel convs on the map before the upsampling
     base_params(p, h->conv_up1);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = kNumFeat; p.out_bf16 = U1; p.ldb = kNumFeat;
-    RUN(conv3(f, "conv_up1", h->conv_up1, U0up, B, 2 * H, 2 * W, kNumFeat, p));
+    RUN(conv3_up(f, "conv_up1", h->conv_up1, U0, B, H, W, p));
     TAP("up1", U1, 1, kNumFeat, 4 * N, kNumFeat);
-    LAUNCH("upsample2", 1, launch_upsample_nearest2(U1, U1up, B, 2 * H, 2 * W, kNumFeat, f.st));
     base_params(p, h->conv_up2);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = kNumFeat; p.out_bf16 = U2; p.ldb = kNumFeat;
-    RUN(conv3(f, "conv_up2", h->conv_up2, U1up, B, 4 * H, 4 * W, kNumFeat, p));
+    RUN(conv3_up(f, "conv_up2", h->conv_up2, U1, B, 2 * H, 2 * W, p));
     TAP("up2", U2, 1, kNumFeat, 16 * N, kNumFeat);
     base_params(p, h->conv_hr);
     p.epi = EPI_STORE; p.act = ACT_LRELU; p.slope = 0.2f; p.n_real = kNumFeat; p.out_bf16 = U3; p.ldb = kNumFeat;

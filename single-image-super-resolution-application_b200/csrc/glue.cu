@@ -191,20 +191,6 @@ __global__ void __launch_bounds__(kDwThreads, 1) dwconv5_kernel(const __grid_con
 
 #endif  // HITSIR_AB_PATHS
 
-// thread = (output pixel, 16-byte chunk)
-__global__ void upsample2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int B, int H, int W, int C) {
-  const int chunks = C / 8;
-  const int OH = 2 * H, OW = 2 * W;
-  const long long total = (long long)B * OH * OW * chunks;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int ch = (int)(idx % chunks);
-    const long long pix = idx / chunks;
-    const int ox = (int)(pix % OW); const long long t = pix / OW; const int oy = (int)(t % OH); const int b = (int)(t / OH);
-    const uint4 u = __ldg(reinterpret_cast<const uint4*>(in + (((long long)b * H + (oy >> 1)) * W + (ox >> 1)) * C + ch * 8));
-    *reinterpret_cast<uint4*>(out + pix * C + ch * 8) = u;
-  }
-}
-
 // PIL-style uint8 HWC image -> [0,1] fp32 NCHW (torchvision to_tensor: true division by 255; reference utils/utils.py:143-145)
 __global__ void u8hwc_to_f32nchw_kernel(const uint8_t* __restrict__ in, float* __restrict__ out, int B, int H, int W, int C) {
   const long long total = (long long)B * C * H * W;
@@ -892,12 +878,6 @@ int launch_dwconv5_gelu_add(const bf16* h1, const float* w, const float* bias, b
   return 0;
 }
 #endif
-int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st) {
-  const long long total = (long long)B * 4 * H * W * (C / 8);
-  upsample2_kernel<<<grid_for(total, 256), 256, 0, st>>>(in, out, B, H, W, C);
-  HITSIR_CHECK(cudaGetLastError());
-  return 0;
-}
 int launch_u8hwc_to_f32nchw(const uint8_t* in, float* out, int B, int H, int W, int C, cudaStream_t st) {
   u8hwc_to_f32nchw_kernel<<<grid_for((long long)B * C * H * W, 256), 256, 0, st>>>(in, out, B, H, W, C);
   HITSIR_CHECK(cudaGetLastError());

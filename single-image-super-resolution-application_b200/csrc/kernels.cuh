@@ -44,8 +44,6 @@ int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const uint8_t* w
 // weights (box {64, 192}), w1 = packed fc1 weights bf16 [384][192], res / xout fp32 [N][180], h1 bf16 [N][384]
 int launch_proj_fc1(const bf16* outsc, const CUtensorMap& tm_wp, const float* bp, const float* gamma, const float* beta, const float* res,
                     float* xout, const bf16* w1, const float* b1, bf16* h1, long long N, int num_sms, cudaStream_t st);
-// nearest x2 upsample of an NHWC bf16 map with C channels
-int launch_upsample_nearest2(const bf16* in, bf16* out, int B, int H, int W, int C, cudaStream_t st);
 int launch_fill_f32(float* p, float v, long long n, cudaStream_t st);
 // per-image mean squared difference of the YCbCr Y channels of two [0,1] fp32 NCHW RGB batches (utils/utils.py:170-186, experiment.py:436-463)
 long long psnr_y_chunks(int H, int W);
@@ -151,6 +149,7 @@ int launch_fusion_combine(const float* first, const float* second, const float* 
 // ---- pack.cu (weight-only precomputation) --------------------------------------------------------
 // conv / linear weight fp32 [Co][Ci][kh][kw] -> bf16 [Npad][taps*Cipad], k = tap*Cipad + ci; bias -> fp32 [Npad]
 // perm_k != 0 (linear only): K index = head-padded position, i.e. wp[n][p] = w[n][scc_chan(p)]
+int launch_pack_subpixel(const float* w, const float* b, bf16* wp, float* bp, cudaStream_t st);   // [64][64][3][3] -> four 2x2 phase filters [64][16*64]
 int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, int perm_k, cudaStream_t st);
 // MultipleSizeConvExtract: conv3/5/7/9 + conv_x embedded in a 9x9x3 footprint, rows grouped per 32 channels x 5 responses (EPI_MSGATE)
 int launch_pack_msconv(const float* w3, const float* w5, const float* w7, const float* w9, const float* wx,

@@ -28,6 +28,29 @@ __global__ void pack_conv_kernel(const float* __restrict__ w, const float* __res
   for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < Npad; n += gridDim.x * blockDim.x) bp[n] = (n < Co && b != nullptr) ? b[n] : 0.f;
 }
 
+// 3x3 conv applied to a x2 nearest-upsampled map == four 2x2 convs on the ORIGINAL map, one per output phase (a, b) = (Y & 1, X & 1):
+// HR row 2y + a + ky - 1 is LR row y + floor((a + ky - 1) / 2), so for a = 0 the taps ky = {0} | {1, 2} fall on rows y - 1 | y and for
+// a = 1 the taps {0, 1} | {2} on rows y | y + 1 (same along x).  The taps that share a source pixel are summed in fp32 and rounded to
+// bf16 once.  Layout [64 co][16 x 64]: column (phase * 4 + dyi * 2 + dxi) * 64 + ci, phase = 2a + b, LR offset dy = a - 1 + dyi.
+// (interpolate(scale_factor=2, mode='nearest') + conv_up1 / conv_up2, /root/reference/models/hit_sir_pro.py:1331-1332)
+__global__ void pack_subpixel_kernel(const float* __restrict__ w, const float* __restrict__ b, bf16* __restrict__ wp, float* __restrict__ bp) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < 64 * 1024) {
+    const int co = idx >> 10, k = idx & 1023;
+    const int t = k >> 6, ci = k & 63;
+    const int ph = t >> 2, dyi = (t >> 1) & 1, dxi = t & 1;
+    const int a = ph >> 1, bb = ph & 1;
+    // tap range of (phase bit, offset index): (0,0) -> {0}, (0,1) -> {1,2}, (1,0) -> {0,1}, (1,1) -> {2}
+    const int ky0 = a == 0 ? (dyi == 0 ? 0 : 1) : (dyi == 0 ? 0 : 2), ky1 = a == 0 ? (dyi == 0 ? 0 : 2) : (dyi == 0 ? 1 : 2);
+    const int kx0 = bb == 0 ? (dxi == 0 ? 0 : 1) : (dxi == 0 ? 0 : 2), kx1 = bb == 0 ? (dxi == 0 ? 0 : 2) : (dxi == 0 ? 1 : 2);
+    float v = 0.f;
+    for (int ky = ky0; ky <= ky1; ++ky)
+      for (int kx = kx0; kx <= kx1; ++kx) v += w[((co * 64 + ci) * 3 + ky) * 3 + kx];
+    wp[idx] = __float2bfloat16(v);
+  }
+  if (idx < 64) bp[idx] = b[idx];
+}
+
 // rows: tile j (0..5) x slot q (0..4: conv3,5,7,9,conv_x) x 32 embedding channels c = 32j + ci (zero rows for c >= 180);
 // K = 9x9 footprint x in_ch.  One 160-row N tile therefore holds all five responses of 32 channels (EPI_MSGATE).
 __global__ void pack_msconv_kernel(const float* __restrict__ w3, const float* __restrict__ w5, const float* __restrict__ w7, const float* __restrict__ w9,
@@ -186,6 +209,11 @@ __global__ void pooled_bias_kernel(const float* __restrict__ tbl, int win, int b
 
 int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, int perm_k, cudaStream_t st) {
   pack_conv_kernel<<<grid_for((long long)Npad * taps * Cipad, 256), 256, 0, st>>>(w, b, wp, bp, Co, Ci, taps, Npad, Cipad, perm_k);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pack_subpixel(const float* w, const float* b, bf16* wp, float* bp, cudaStream_t st) {
+  pack_subpixel_kernel<<<64 * 1024 / 256, 256, 0, st>>>(w, b, wp, bp);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

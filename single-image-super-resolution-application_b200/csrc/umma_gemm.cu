@@ -226,6 +226,24 @@ int make_tmap_nhwc_t(CUtensorMap* m, const void* base, int elem_bytes, int B, in
   return 0;
 }
 
+int make_tmap_nhwc_strided(CUtensorMap* m, const void* base, int B, int H, int W, int C, uint64_t pix_bytes, uint64_t row_bytes, uint64_t img_bytes,
+                           uint32_t box_c, uint32_t box_w, uint32_t box_h) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return 1;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {pix_bytes, row_bytes, img_bytes};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(strided nhwc B=%d H=%d W=%d C=%d) failed with CUresult %d", B, H, W, C, (int)r);
+    return 1;
+  }
+  return 0;
+}
+
 // 2-D map without shared-memory swizzle (dense box rows)
 int make_tmap_2d_plain(CUtensorMap* m, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
                        uint32_t box_inner, uint32_t box_outer) {

@@ -1,26 +1,33 @@
-"""Rewrite the per-tap bound tables of tests/helpers.py from a measurement of tools/measure_taps.py:  bound = 1.5 x measured.
+"""Rewrite the per-tap bound tables of tests/helpers.py from measurements of tools/measure_taps.py:
 
-    python tools/update_bounds.py gpurun_out/taps.json
+    python tools/update_bounds.py gpurun_out/taps_build_a.json [gpurun_out/taps_build_b.json ...]
+
+bound = 1.5 x the LARGEST error measured over the listed builds.  One build is not enough for the large-window taps: with the
+"stress" weights a 1e-7 relative change of any upstream value (another GELU or sigmoid formulation, both far below the bf16 step)
+flips bf16 roundings, and the error of the w = 32 / 48 / 64 self-correlation taps then moves by up to 2x in either direction while
+every tap before them agrees to four digits (builds r2a / r2m / r2p: ssc5 2.1e-2 / 1.1e-2 / 2.0e-2, ssc4 9.5e-3 / 5.0e-3 / 5.7e-3).
 """
 import json
 import re
 import sys
 
 path = "tests/helpers.py"
-m = json.load(open(sys.argv[1]))
+ms = [json.load(open(a)) for a in sys.argv[1:]]
 src = open(path).read()
 
 
-def fix(table, key, val, txt):
-    pat = re.compile(r'(    "%s": )([0-9.e+-]+)(,\s*# measured )([0-9.e+-]+)' % re.escape(key))
-    new, n = pat.subn(lambda g: "%s%.2e%s%.2e" % (g.group(1), 1.5 * val, g.group(3), val), txt)
+def fix(table, key, vals, txt):
+    pat = re.compile(r'(    "%s": )([0-9.e+-]+)(,\s*# measured )([0-9.e+-]+(?: \.\. [0-9.e+-]+)?)' % re.escape(key))
+    lo, hi = min(vals), max(vals)
+    meas = "%.2e" % hi if len(vals) == 1 or "%.2e" % lo == "%.2e" % hi else "%.2e .. %.2e" % (lo, hi)
+    new, n = pat.subn(lambda g: "%s%.2e%s%s" % (g.group(1), 1.5 * hi, g.group(3), meas), txt)
     assert n == 1, (table, key, n)
     return new
 
 
-for k, v in m["taps"].items():
-    src = fix("TAP_BOUNDS", k, v, src)
-for k, v in m["scc_parts"].items():
-    src = fix("SCC_PART_BOUNDS", k, v, src)
+for k in ms[-1]["taps"]:
+    src = fix("TAP_BOUNDS", k, [m["taps"][k] for m in ms if k in m["taps"]], src)
+for k in ms[-1]["scc_parts"]:
+    src = fix("SCC_PART_BOUNDS", k, [m["scc_parts"][k] for m in ms if k in m.get("scc_parts", {})], src)
 open(path, "w").write(src)
-print("updated", len(m["taps"]) + len(m["scc_parts"]), "bounds")
+print("updated", len(ms[-1]["taps"]) + len(ms[-1]["scc_parts"]), "bounds from", len(ms), "build(s)")
