@@ -16,18 +16,28 @@ namespace hitsir {
 namespace {
 
 constexpr int kATile = 160 * 128;          // (8 + 2) rows x 16 pixels x 64 ch bf16
-constexpr int kAStages = 4;
+// halo boxes in flight per SM: the A stream comes from L2 at ~1.5 us per box, so the ring depth (x 20 KB) is what sets its bandwidth.
+// BN = 16 (conv_last, 18 KB of filters) has room for 9 stages, BN = 64 (72 KB of filters + 3 output boxes) for 5.
+#ifndef HITSIR_C64_STAGES16
+#define HITSIR_C64_STAGES16 9
+#endif
+#ifndef HITSIR_C64_STAGES64
+#define HITSIR_C64_STAGES64 5
+#endif
 constexpr int kBoxBytes = 128 * 128;
 constexpr int kNBox = 3;
 
 template <int BN>
 struct Cfg {
+  static constexpr int kAStages = BN == 64 ? HITSIR_C64_STAGES64 : HITSIR_C64_STAGES16;
   static constexpr int kBBytes = 9 * BN * 128;                      // resident filter bank
   static constexpr int kOffA = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kOffBox = kOffA + kAStages * kATile;
   static constexpr int kOffBias = kOffBox + (BN == 64 ? kNBox * kBoxBytes : 0);
   static constexpr int kOffBars = kOffBias + 64 * 4;
   static constexpr int kSmemBytes = kOffBars + 32 * 8 + 16 + 1024;
+  static_assert(2 * kAStages + 4 + 2 * kNBox + 1 <= 32, "barrier slots");
+  static_assert(kSmemBytes <= 232448, "smem budget");
   static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : 128;
 };
 
@@ -44,6 +54,7 @@ __global__ void __launch_bounds__(384, 1)
 conv3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o,
                  const GemmParams p) {
   using C = Cfg<BN>;
+  constexpr int kAStages = C::kAStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sp = smem_raw + (sb - smem_u32(smem_raw));
@@ -375,6 +386,159 @@ conv3_c64_up_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_con
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// conv_last (64 -> in_chans <= 4, :1334 / :1241) with the nine taps folded into the N dimension.  The plain kernel issues 36 MMAs of
+// N = 16 per 128 output pixels, and a tcgen05.mma with shared-memory A costs ~53 cycles however small N is (ncu: tensor-core pipe busy
+// 73 %, math 12 %, profiles/r2_ncu_full_hr_convs_summary.csv).  Here every INPUT pixel q of an (6+2) x (30+2) halo tile is multiplied
+// once by all taps, P[q][tap][co] = a_q . w[co][:][tap] (one [256 x 64] x [64 x 48] contraction = 8 MMAs), and the epilogue adds the nine
+// shifted partial products per output pixel from shared memory: out[y][x][co] = b[co] + sum_t P[(y+ky, x+kx)][t][co].  8 instead of
+// 50 MMAs per 180 outputs, and one 32 KB halo box per tile instead of three 20 KB ones (1.4x instead of 3.75x re-fetch).
+constexpr int kFoldTW = 30, kFoldTH = 6;                // output tile; halo box 32 x 8 pixels = 256 rows = two M blocks
+constexpr int kFoldA = 256 * 128;
+constexpr int kFoldStages = 4;
+constexpr int kFoldN = 48;                              // 9 taps x 4 output channels, padded to a multiple of 16
+constexpr int kFoldPRow = 36;                           // floats per halo pixel in the partial-product buffer (144 B: float4 accesses of a quarter warp hit 32 banks)
+struct FoldCfg {
+  static constexpr int kBBytes = kFoldN * 128;
+  static constexpr int kOffA = kBBytes;                                       // 6144: 1024-byte aligned
+  static constexpr int kOffP = kOffA + kFoldStages * kFoldA;
+  static constexpr int kOffBars = kOffP + 2 * 256 * kFoldPRow * 4;
+  static constexpr int kSmemBytes = kOffBars + 16 * 8 + 16 + 1024;
+};
+static_assert(FoldCfg::kSmemBytes <= 232448 && FoldCfg::kOffA % 1024 == 0, "smem budget / alignment");
+
+__global__ void __launch_bounds__(384, 1)
+conv_last_fold_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmParams p) {
+  using C = FoldCfg;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* sp = smem_raw + (sb - smem_u32(smem_raw));
+  const uint32_t bar0 = sb + C::kOffBars;
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (kFoldStages + s); };
+  auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * kFoldStages + s); };
+  auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * kFoldStages + 2 + s); };
+  const uint32_t b_full = bar0 + 8u * (2 * kFoldStages + 4);
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(sp + C::kOffBars + 16 * 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = p.m_tiles;
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kFoldStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
+    mbar_init(b_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc(smem_u32(tmem_ptr_smem), 256); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  auto tile_xyb = [&](int t, int* x0, int* y0, int* b) {
+    const int tx = t % p.tiles_x; const int t2 = t / p.tiles_x;
+    *x0 = tx * kFoldTW; *y0 = (t2 % p.tiles_y) * kFoldTH; *b = t2 / p.tiles_y;
+  };
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ===================== producer: folded filters once, then one halo box per tile =====================
+      mbar_expect_tx(b_full, (uint32_t)C::kBBytes);
+      tma_load_2d(sb, &tmap_b, b_full, 0, 0);
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++cnt) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        const int s = (int)(cnt % kFoldStages);
+        mbar_wait(empty_bar(s), ((cnt / kFoldStages) & 1u) ^ 1u);
+        mbar_expect_tx(full_bar(s), kFoldA);
+        tma_load_4d(sb + C::kOffA + s * kFoldA, &tmap_a, full_bar(s), 0, x0 - 1, y0 - 1 + p.a_y_off, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ===================== MMA issuer: P[256 x 48] = A[256 x 64] Wfold^T, two M blocks x four k-steps =====================
+      constexpr uint32_t idesc = umma_idesc_bf16(128, kFoldN);
+      mbar_wait(b_full, 0u);
+      const uint64_t bdesc = umma_desc_sw128(sb);
+      uint32_t cnt = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++cnt) {
+        const int as = (int)(cnt & 1u);
+        const int s = (int)(cnt % kFoldStages);
+        mbar_wait(tempty_bar(as), ((cnt >> 1) & 1u) ^ 1u);
+        mbar_wait(full_bar(s), (cnt / kFoldStages) & 1u);
+        tc_fence_after();
+        const uint32_t sa = sb + C::kOffA + s * kFoldA;
+#pragma unroll
+        for (int mb = 0; mb < 2; ++mb) {
+          const uint64_t adesc = umma_desc_sw128(sa + mb * 16384);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + (uint32_t)(as * 2 * kFoldN + mb * kFoldN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, k != 0 ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+        umma_commit(tfull_bar(as));
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (8 warps): partial products TMEM -> shared memory, then 9-tap gather per output pixel =====================
+    const int q = warp & 3, mb = (warp - 4) >> 2;
+    const int row = mb * 128 + q * 32 + lane;                // halo pixel of this thread in step 1
+    const int tid = threadIdx.x - 128;                       // output pixel of this thread in step 2 (first 180 threads)
+    const int oy = tid / kFoldTW, ox = tid - oy * kFoldTW;
+    float bias[4], mean[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { bias[c] = c < p.n_real ? p.bias[c] : 0.f; mean[c] = p.mean[c]; }
+    uint32_t cnt = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++cnt) {
+      const int as = (int)(cnt & 1u);
+      float* P = reinterpret_cast<float*>(sp + C::kOffP) + (size_t)as * 256 * kFoldPRow;
+      mbar_wait(tfull_bar(as), (cnt >> 1) & 1u);
+      tc_fence_after();
+      {
+        const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * 2 * kFoldN + mb * kFoldN);
+        uint32_t r0[16], r1[16], r2[16];
+        tmem_ld16_nw(tacc, r0); tmem_ld16_nw(tacc + 16, r1); tmem_ld16_nw(tacc + 32, r2);
+        tmem_ld_wait();
+        reg_fence16(r0); reg_fence16(r1); reg_fence16(r2);
+        tc_fence_before();
+        mbar_arrive_warp(tempty_bar(as));
+        uint4* dst = reinterpret_cast<uint4*>(P + (size_t)row * kFoldPRow);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(r0[4 * i], r0[4 * i + 1], r0[4 * i + 2], r0[4 * i + 3]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[4 + i] = make_uint4(r1[4 * i], r1[4 * i + 1], r1[4 * i + 2], r1[4 * i + 3]);
+        dst[8] = make_uint4(r2[0], r2[1], r2[2], r2[3]);      // columns 32..35 = tap 8; 36..47 are padding
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");          // the eight epilogue warps only; P is double-buffered by tile parity
+      if (tid < kFoldTW * kFoldTH) {
+        int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
+        const int y = y0 + oy, x = x0 + ox;
+        float4 acc = make_float4(bias[0], bias[1], bias[2], bias[3]);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 v = *reinterpret_cast<const float4*>(P + (size_t)((oy + ky) * 32 + ox + kx) * kFoldPRow + (ky * 3 + kx) * 4);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+          }
+        if (y < p.H && x < p.W) {
+          const float o[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            if (c < p.n_real) p.out_f32[(((long long)b * p.shuf_c + c) * p.H + y) * p.W + x] = o[c] * p.out_scale + mean[c];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 template <int BN>
 int launch_bn(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, int num_sms, cudaStream_t st) {
   using C = Cfg<BN>;
@@ -417,6 +581,24 @@ int launch_conv3_c64_up(const GemmParams& p, const bf16* A, const CUtensorMap& t
   const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
   if (grid <= 0) return 0;
   conv3_c64_up_kernel<<<grid, 384, UpCfg::kSmemBytes, st>>>(ta, tb, to[0], to[1], to[2], to[3], p);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+
+// conv_last with folded taps: A NHWC bf16 [B,H,W,64]; tb: folded filters [48][64] (row = tap * 4 + co) with a {64, 48} box; out_f32 NCHW image
+int launch_conv_last_fold(const GemmParams& p0, const bf16* A, const CUtensorMap& tb, int num_sms, cudaStream_t st) {
+  static unsigned long long configured = 0;
+  if (ensure_dynamic_smem(conv_last_fold_kernel, FoldCfg::kSmemBytes, &configured)) return 1;
+  GemmParams p = p0;
+  p.tiles_x = (p.W + kFoldTW - 1) / kFoldTW; p.tiles_y = (p.H + kFoldTH - 1) / kFoldTH;
+  const long long total = (long long)p.B * p.tiles_x * p.tiles_y;
+  if (total > 2147483647LL) { set_error("launch_conv_last_fold: too many tiles"); return 1; }
+  p.m_tiles = (int)total;
+  CUtensorMap ta;
+  if (make_tmap_nhwc(&ta, A - (size_t)p.a_y_off * p.W * 64, p.B, p.H + 2 * p.a_y_off, p.W, 64, 64, 32, 8)) return 1;
+  const int grid = p.m_tiles < num_sms ? p.m_tiles : num_sms;
+  if (grid <= 0) return 0;
+  conv_last_fold_kernel<<<grid, 384, FoldCfg::kSmemBytes, st>>>(ta, tb, p);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

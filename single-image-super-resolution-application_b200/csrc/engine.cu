@@ -36,6 +36,8 @@ struct GemmW {
   float* b = nullptr;
   int Npad = 0, K = 0, BN = 0;
   CUtensorMap tm;
+  bf16* wf = nullptr;          // conv_last 64 -> in_chans only: the nine taps folded into N, [48][64] (launch_conv_last_fold)
+  CUtensorMap tmf;
 };
 
 struct BlockW {
@@ -350,6 +352,14 @@ int make_subpixel_w(HitsirHandle* h, GemmW* g, const std::string& prefix, cudaSt
   return make_tmap_2d(&g->tm, g->w, (uint64_t)g->K, 64, (uint64_t)g->K * 2, 64, 64);
 }
 
+// conv_last over a 64-channel map: additionally the folded-tap operand of conv_last_fold_kernel
+int make_last_w(HitsirHandle* h, GemmW* g, int ic, cudaStream_t st) {
+  if (make_gemm_w(h, g, "conv_last", ic, kNumFeat, 9, st)) return 1;
+  if (dev_alloc(h, &g->wf, (size_t)48 * 64)) return 1;
+  if (launch_pack_fold_last(P(h, "conv_last.weight"), g->wf, ic, st)) return 1;
+  return make_tmap_2d(&g->tmf, g->wf, 64, 48, 128, 64, 48);
+}
+
 void free_owned(HitsirHandle* h) {
   for (void* p : h->owned) cudaFree(p);
   h->owned.clear(); h->chunk_bytes.clear();
@@ -494,7 +504,7 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
         h->upsample.resize(1);
         if (make_gemm_w(h, &h->upsample[0], "upsample.0", 9 * kNumFeat, kNumFeat, 9, st)) return 1;
       }
-      if (make_gemm_w(h, &h->conv_last, "conv_last", ic, kNumFeat, 9, st)) return 1;
+      if (make_last_w(h, &h->conv_last, ic, st)) return 1;
       break;
     }
     case HITSIR_UP_PIXELSHUFFLEDIRECT:
@@ -506,7 +516,7 @@ int finalize(HitsirHandle* h, cudaStream_t st) {
       if (make_subpixel_w(h, &h->conv_up1, "conv_up1", st)) return 1;
       if (make_subpixel_w(h, &h->conv_up2, "conv_up2", st)) return 1;
       if (make_gemm_w(h, &h->conv_hr, "conv_hr", kNumFeat, kNumFeat, 9, st)) return 1;
-      if (make_gemm_w(h, &h->conv_last, "conv_last", ic, kNumFeat, 9, st)) return 1;
+      if (make_last_w(h, &h->conv_last, ic, st)) return 1;
       break;
     default:
       if (make_gemm_w(h, &h->conv_last, "conv_last", ic, C, 9, st)) return 1;
@@ -769,6 +779,7 @@ int conv3(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, 
        (w.BN == 16 && p.epi == EPI_SHUFFLE_NCHW && p.ps == 1 && p.n_real <= 4))) {
     ProfScope ps(f.h, f.st, cat);
     f.h->launches++;
+    if (w.BN == 16 && w.wf != nullptr && p.res_img == nullptr) return launch_conv_last_fold(p, A, w.tmf, f.h->num_sms, f.st);
     return launch_conv3_c64(w.BN, p, A, w.tm, f.h->num_sms, f.st);
   }
   CUtensorMap maps[5];

@@ -272,6 +272,8 @@ int make_tmap_nhwc_strided(CUtensorMap* m, const void* base, int B, int H, int W
                            uint32_t box_c, uint32_t box_w, uint32_t box_h);
 // x2 nearest upsampling + 3x3 conv 64 -> 64 + bias + LeakyReLU as four 2x2 phase convs on the LR map (conv3_c64.cu); A [B,H,W,64], out [B,2H,2W,64]
 int launch_conv3_c64_up(const GemmParams& p, const bf16* A, const CUtensorMap& tb, int num_sms, cudaStream_t st);
+// conv_last 64 -> n_real <= 4 with the nine taps folded into N (conv3_c64.cu); tb = folded filters [48][64], out_f32 NCHW (EPI_SHUFFLE_NCHW, ps = 1)
+int launch_conv_last_fold(const GemmParams& p, const bf16* A, const CUtensorMap& tb, int num_sms, cudaStream_t st);
 int launch_conv3_c64(int BN, const GemmParams& p, const bf16* A, const CUtensorMap& tb, int num_sms, cudaStream_t st);
 int launch_umma_gemm_tma(int BN, const GemmParams& p, const CUtensorMap* maps, int num_sms, cudaStream_t st);
 int launch_umma_gemm(int BN, const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb, int num_sms, cudaStream_t st);

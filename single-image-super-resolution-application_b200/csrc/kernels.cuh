@@ -150,6 +150,7 @@ int launch_fusion_combine(const float* first, const float* second, const float* 
 // conv / linear weight fp32 [Co][Ci][kh][kw] -> bf16 [Npad][taps*Cipad], k = tap*Cipad + ci; bias -> fp32 [Npad]
 // perm_k != 0 (linear only): K index = head-padded position, i.e. wp[n][p] = w[n][scc_chan(p)]
 int launch_pack_subpixel(const float* w, const float* b, bf16* wp, float* bp, cudaStream_t st);   // [64][64][3][3] -> four 2x2 phase filters [64][16*64]
+int launch_pack_fold_last(const float* w, bf16* wp, int Co, cudaStream_t st);   // [Co<=4][64][3][3] -> [48][64], row = tap * 4 + co
 int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co, int Ci, int taps, int Npad, int Cipad, int perm_k, cudaStream_t st);
 // MultipleSizeConvExtract: conv3/5/7/9 + conv_x embedded in a 9x9x3 footprint, rows grouped per 32 channels x 5 responses (EPI_MSGATE)
 int launch_pack_msconv(const float* w3, const float* w5, const float* w7, const float* w9, const float* wx,

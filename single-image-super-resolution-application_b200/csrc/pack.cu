@@ -51,6 +51,17 @@ __global__ void pack_subpixel_kernel(const float* __restrict__ w, const float* _
   if (idx < 64) bp[idx] = b[idx];
 }
 
+// conv_last 64 -> Co <= 4 with the taps folded into N: row tap * 4 + co of [48][64] holds w[co][:][tap] (rows with co >= Co and rows 36.. are zero)
+__global__ void pack_fold_last_kernel(const float* __restrict__ w, bf16* __restrict__ wp, int Co) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 48 * 64) return;
+  const int n = idx >> 6, ci = idx & 63;
+  const int tap = n >> 2, co = n & 3;
+  float v = 0.f;
+  if (tap < 9 && co < Co) v = w[(co * 64 + ci) * 9 + tap];
+  wp[idx] = __float2bfloat16(v);
+}
+
 // rows: tile j (0..5) x slot q (0..4: conv3,5,7,9,conv_x) x 32 embedding channels c = 32j + ci (zero rows for c >= 180);
 // K = 9x9 footprint x in_ch.  One 160-row N tile therefore holds all five responses of 32 channels (EPI_MSGATE).
 __global__ void pack_msconv_kernel(const float* __restrict__ w3, const float* __restrict__ w5, const float* __restrict__ w7, const float* __restrict__ w9,
@@ -214,6 +225,11 @@ int launch_pack_conv(const float* w, const float* b, bf16* wp, float* bp, int Co
 }
 int launch_pack_subpixel(const float* w, const float* b, bf16* wp, float* bp, cudaStream_t st) {
   pack_subpixel_kernel<<<64 * 1024 / 256, 256, 0, st>>>(w, b, wp, bp);
+  HITSIR_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_pack_fold_last(const float* w, bf16* wp, int Co, cudaStream_t st) {
+  pack_fold_last_kernel<<<48 * 64 / 256, 256, 0, st>>>(w, wp, Co);
   HITSIR_CHECK(cudaGetLastError());
   return 0;
 }

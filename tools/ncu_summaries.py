@@ -21,7 +21,11 @@ COLS = ["launch__grid_size", "launch__block_size", "launch__registers_per_thread
         "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
         "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg"]
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "smsp__cycles_active.avg",
+        # tcgen05 side (only in --set full reports): cycles the tensor-core pipe is occupied by tcgen05.mma (operand fetch included; small-N
+        # instructions keep it busy without filling the math units) and its shared-memory operand reads
+        "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+        "lts__t_bytes.sum", "l1tex__m_xbar2l1tex_read_bytes.sum"]
 CATEGORY = {"ffn_tail_kernel": "ffn_tail", "qkv_casa_mma_kernel": "qkv_build", "qkv_casa_kernel": "qkv_build", "scc_dense_kernel<16>": "scc_w4",
             "scc_dense_kernel<64>": "scc_w8"}
 
