@@ -7,8 +7,8 @@
 //     ky*16+127 are the A operand of tap (ky, kx) (descriptor start + ky * 2 KB, still 1024-byte aligned).  Every input pixel
 //     is therefore fetched 3.75x per tile instead of 9x; the generic kernel was bound by L2->SM traffic (~10 TB/s), not by HBM.
 // Out-of-image taps are TMA out-of-bounds zero fill (= the conv's zero padding).
-// BN = 64: bias + LeakyReLU -> bf16 NHWC via a swizzled box and TMA store.  BN = 16: conv_last, n_real <= 4 output channels,
-// de-normalised (x / img_range + mean, :1342) and written straight to the NCHW fp32 image.
+// bias + LeakyReLU -> bf16 NHWC via a swizzled box and TMA store.  (conv_last, 64 -> in_chans, has its own kernel below: with N = 16
+// this one spent 36 tensor-core instructions of ~53 cycles on 128 pixels.)
 #include "gemm.cuh"
 
 namespace hitsir {
@@ -16,29 +16,21 @@ namespace hitsir {
 namespace {
 
 constexpr int kATile = 160 * 128;          // (8 + 2) rows x 16 pixels x 64 ch bf16
-// halo boxes in flight per SM: the A stream comes from L2 at ~1.5 us per box, so the ring depth (x 20 KB) is what sets its bandwidth.
-// BN = 16 (conv_last, 18 KB of filters) has room for 9 stages, BN = 64 (72 KB of filters + 3 output boxes) for 5.
-#ifndef HITSIR_C64_STAGES16
-#define HITSIR_C64_STAGES16 9
-#endif
-#ifndef HITSIR_C64_STAGES64
-#define HITSIR_C64_STAGES64 5
-#endif
+constexpr int kAStages = 4;                // deeper rings (5, 9) measured no faster: the kernel is bound by the tcgen05 pipe (72 % busy), not by the ring
 constexpr int kBoxBytes = 128 * 128;
 constexpr int kNBox = 3;
 
 template <int BN>
 struct Cfg {
-  static constexpr int kAStages = BN == 64 ? HITSIR_C64_STAGES64 : HITSIR_C64_STAGES16;
   static constexpr int kBBytes = 9 * BN * 128;                      // resident filter bank
   static constexpr int kOffA = (kBBytes + 1023) / 1024 * 1024;
   static constexpr int kOffBox = kOffA + kAStages * kATile;
-  static constexpr int kOffBias = kOffBox + (BN == 64 ? kNBox * kBoxBytes : 0);
+  static constexpr int kOffBias = kOffBox + kNBox * kBoxBytes;
   static constexpr int kOffBars = kOffBias + 64 * 4;
   static constexpr int kSmemBytes = kOffBars + 32 * 8 + 16 + 1024;
   static_assert(2 * kAStages + 4 + 2 * kNBox + 1 <= 32, "barrier slots");
   static_assert(kSmemBytes <= 232448, "smem budget");
-  static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : 128;
+  static constexpr int kTmemCols = 128;
 };
 
 __device__ __forceinline__ void tma_store_4d(const void* tmap, uint32_t src, int c0, int c1, int c2, int c3) {
@@ -54,7 +46,6 @@ __global__ void __launch_bounds__(384, 1)
 conv3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const __grid_constant__ CUtensorMap tmap_o,
                  const GemmParams p) {
   using C = Cfg<BN>;
-  constexpr int kAStages = C::kAStages;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t sb = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sp = smem_raw + (sb - smem_u32(smem_raw));
@@ -71,7 +62,7 @@ conv3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = p.m_tiles;
-  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); if (BN == 64) tma_prefetch_desc(&tmap_o); }
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&tmap_a); tma_prefetch_desc(&tmap_b); tma_prefetch_desc(&tmap_o); }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kAStages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(tfull_bar(s), 1); mbar_init(tempty_bar(s), 8); }
@@ -137,7 +128,7 @@ conv3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == 3) {
-    if (BN == 64 && lane == 0) {
+    if (lane == 0) {
       // ===================== TMA store of finished boxes =====================
       uint32_t u = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++u) {
@@ -162,40 +153,23 @@ conv3_c64_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_wait(tfull_bar(as), ((uint32_t)(it >> 1)) & 1u);
       tc_fence_after();
       const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      if constexpr (BN == 64) {
-        float v[32];
-        tmem_ld32(tacc + 32 * hs, v);
-        tc_fence_before();
-        mbar_arrive_warp(tempty_bar(as));
+      float v[32];
+      tmem_ld32(tacc + 32 * hs, v);
+      tc_fence_before();
+      mbar_arrive_warp(tempty_bar(as));
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { const float x = v[i] + s_bias[32 * hs + i]; v[i] = p.act == ACT_LRELU ? lrelu(x, p.slope) : x; }
-        const int s = (int)(u % kNBox);
-        if (u >= (uint32_t)kNBox) mbar_wait(box_free(s), ((u / kNBox) - 1u) & 1u);
-        uint8_t* row = sp + C::kOffBox + s * kBoxBytes + r * 128;
+      for (int i = 0; i < 32; ++i) { const float x = v[i] + s_bias[32 * hs + i]; v[i] = p.act == ACT_LRELU ? lrelu(x, p.slope) : x; }
+      const int s = (int)(u % kNBox);
+      if (u >= (uint32_t)kNBox) mbar_wait(box_free(s), ((u / kNBox) - 1u) & 1u);
+      uint8_t* row = sp + C::kOffBox + s * kBoxBytes + r * 128;
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          const uint4 o = make_uint4(pack_bf16x2(v[8 * ch], v[8 * ch + 1]), pack_bf16x2(v[8 * ch + 2], v[8 * ch + 3]),
-                                     pack_bf16x2(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16x2(v[8 * ch + 6], v[8 * ch + 7]));
-          *reinterpret_cast<uint4*>(row + (((uint32_t)(4 * hs + ch) ^ (uint32_t)(r & 7)) << 4)) = o;
-        }
-        fence_proxy_async_smem();
-        mbar_arrive_warp(box_ready(s));
-      } else {
-        // conv_last: columns [0, n_real) -> NCHW fp32 image, x / img_range + mean (:1342); lanes = 16 consecutive x per image row
-        float v[16];
-        if (hs == 0) tmem_ld16(tacc, v);
-        tc_fence_before();
-        mbar_arrive_warp(tempty_bar(as));
-        if (hs == 0) {
-          int x0, y0, b; tile_xyb(t, &x0, &y0, &b);
-          const int y = y0 + (r >> 4), x = x0 + (r & 15);
-          if (y < p.H && x < p.W) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c)
-              if (c < p.n_real) p.out_f32[(((long long)b * p.shuf_c + c) * p.H + y) * p.W + x] = (v[c] + s_bias[c]) * p.out_scale + p.mean[c];
-          }
-        }
+      for (int ch = 0; ch < 4; ++ch) {
+        const uint4 o = make_uint4(pack_bf16x2(v[8 * ch], v[8 * ch + 1]), pack_bf16x2(v[8 * ch + 2], v[8 * ch + 3]),
+                                   pack_bf16x2(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16x2(v[8 * ch + 6], v[8 * ch + 7]));
+        *reinterpret_cast<uint4*>(row + (((uint32_t)(4 * hs + ch) ^ (uint32_t)(r & 7)) << 4)) = o;
       }
+      fence_proxy_async_smem();
+      mbar_arrive_warp(box_ready(s));
     }
   }
   tc_fence_before();
@@ -553,19 +527,14 @@ int launch_bn(const GemmParams& p, const CUtensorMap& ta, const CUtensorMap& tb,
 
 }  // namespace
 
-// A: NHWC bf16 [B,H,W,64]; tb: packed weights [BN][576] with a {64, BN} box; BN = 64 -> out_bf16 [B,H,W,64], BN = 16 -> out_f32 NCHW
+// A: NHWC bf16 [B,H,W,64]; tb: packed weights [64][576] with a {64, 64} box; out_bf16 [B,H,W,64]
 int launch_conv3_c64(int BN, const GemmParams& p, const bf16* A, const CUtensorMap& tb, int num_sms, cudaStream_t st) {
   CUtensorMap ta, to;
+  if (BN != 64) { set_error("launch_conv3_c64: unsupported N tile %d", BN); return 1; }
   // band mode: A points at image row 0 of a buffer that has a_y_off valid halo rows above and below (engine.cu conv3)
   if (make_tmap_nhwc(&ta, A - (size_t)p.a_y_off * p.W * 64, p.B, p.H + 2 * p.a_y_off, p.W, 64, 64, 16, 10)) return 1;
-  to = ta;
-  if (BN == 64) {
-    if (make_tmap_nhwc(&to, p.out_bf16, p.B, p.H, p.W, 64, 64, 16, 8)) return 1;
-    return launch_bn<64>(p, ta, tb, to, num_sms, st);
-  }
-  if (BN == 16) return launch_bn<16>(p, ta, tb, to, num_sms, st);
-  set_error("launch_conv3_c64: unsupported N tile %d", BN);
-  return 1;
+  if (make_tmap_nhwc(&to, p.out_bf16, p.B, p.H, p.W, 64, 64, 16, 8)) return 1;
+  return launch_bn<64>(p, ta, tb, to, num_sms, st);
 }
 
 // A: NHWC bf16 [B,H,W,64] (the LR map; band mode: a_y_off valid halo rows above and below); tb: phase filters [64][1024] with a {64, 64} box;

@@ -776,10 +776,10 @@ int conv3(Fwd& f, const char* cat, const GemmW& w, const bf16* A, int B, int H, 
   // 64-channel inputs (HR stage): resident filter bank + kx-shared halo boxes (conv3_c64.cu)
   if (!f.h->simt && !f.h->direct_epilogue && Cpad == 64 && p.res == nullptr && p.out2_f32 == nullptr &&
       ((w.BN == 64 && p.epi == EPI_STORE && p.out_bf16 != nullptr && p.out_f32 == nullptr && p.ldb == 64) ||
-       (w.BN == 16 && p.epi == EPI_SHUFFLE_NCHW && p.ps == 1 && p.n_real <= 4))) {
+       (w.BN == 16 && w.wf != nullptr && p.res_img == nullptr && p.epi == EPI_SHUFFLE_NCHW && p.ps == 1 && p.n_real <= 4))) {
     ProfScope ps(f.h, f.st, cat);
     f.h->launches++;
-    if (w.BN == 16 && w.wf != nullptr && p.res_img == nullptr) return launch_conv_last_fold(p, A, w.tmf, f.h->num_sms, f.st);
+    if (w.BN == 16) return launch_conv_last_fold(p, A, w.tmf, f.h->num_sms, f.st);
     return launch_conv3_c64(w.BN, p, A, w.tm, f.h->num_sms, f.st);
   }
   CUtensorMap maps[5];
