@@ -179,6 +179,30 @@ __device__ __forceinline__ void mbar_wait_park(uint32_t bar, uint32_t parity, ui
       "DONE:\n\t"
       "}" ::"r"(bar), "r"(parity), "r"(hint_ns) : "memory");
 }
+// Programmatic dependent launch (the per-block chain casa gate -> SCC -> proj -> fc1 -> FFN tail -> pool MLP is 6 dependent launches x 36
+// blocks; on small inputs the grid launch latency between them is a sixth of the forward).  A kernel launched with launch_pdl() may
+// become resident while its predecessor in the stream is still draining; pdl_entry() holds it until that grid has completed and its
+// writes are visible, then lets the NEXT launch in the stream do the same.  Everything before pdl_entry() may only touch memory that no
+// kernel of the forward writes (weights, shared memory, TMEM, barriers).  Kernels launched without the attribute see a no-op.
+#ifndef HITSIR_PDL
+#define HITSIR_PDL 1
+#endif
+__device__ __forceinline__ void pdl_entry() {
+#if HITSIR_PDL
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = HITSIR_PDL ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }

@@ -144,6 +144,7 @@ ffn_tail_kernel(const __grid_constant__ CUtensorMap tm_h1, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_entry();                                           // up to here only weights (fc2 bias, norm2) were read
 
   auto tile_xyb = [&](int t, int* x0, int* y0, int* b) {
     const int tx = t % p.tiles_x; const int t2 = t / p.tiles_x;
@@ -544,8 +545,7 @@ int launch_ffn_tail(const bf16* h1, const uint32_t* dw_tbl_mma, const uint8_t* w
   if (make_tmap_nhwc(&tm_h1, h1 - (size_t)p.h1_y_off * W * kHidp, B, H + 2 * p.h1_y_off, W, kHidp, 64, kBoxW, kBoxH)) return 1;
   if (make_tmap_nhwc_t(&tm_x, x, 4, B, H, W, kC, kC, 32, 16, 8)) return 1;
   const int grid = p.total < num_sms ? p.total : num_sms;
-  ffn_tail_kernel<<<grid, 640, kSmemBytes, st>>>(tm_h1, tm_x, p);
-  HITSIR_CHECK(cudaGetLastError());
+  HITSIR_CHECK(launch_pdl(ffn_tail_kernel, dim3(grid), dim3(640), kSmemBytes, st, tm_h1, tm_x, p));
   return 0;
 }
 

@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(256) sca_stats_kernel(const float* __restrict_
 __global__ void __launch_bounds__(768) sca_mlp_kernel(const float* __restrict__ part_sum, const float* __restrict__ part_max, int nparts, PadGeom g,
                                                       CasaW w, float* __restrict__ s1, float* __restrict__ s2) {
   __shared__ float ps[4][kCp], pm[4][kCp], avg[kC], mx[kC], h1[18], h2[18];
+  pdl_entry();
   const int b = blockIdx.x, grp = threadIdx.x / 192, c = threadIdx.x - grp * 192;
   if (c < kC) {
     float s = 0.f, m = -INFINITY;
@@ -542,6 +543,7 @@ __global__ void casa_bfrag_kernel(CasaW w, uint32_t* __restrict__ img) {
 __global__ void __launch_bounds__(128, QKV_MIN_CTAS) qkv_casa_mma_kernel(const float* __restrict__ x, PadGeom g, const float* __restrict__ cavg,
                                                            const float* __restrict__ cmax, const float* __restrict__ s1, const float* __restrict__ s2,
                                                            const uint32_t* __restrict__ bfrag, bf16* __restrict__ t) {
+  pdl_entry();
   extern __shared__ __align__(16) uint8_t smem_casa[];
   float* xs = reinterpret_cast<float*>(smem_casa);                       // [run][184]
   uint32_t* os = reinterpret_cast<uint32_t*>(xs + kMmaRun * kMmaXS);     // [run][100]
@@ -941,8 +943,7 @@ int launch_reduce_parts(const float* part_sum, const float* part_max, int nparts
   return 0;
 }
 int launch_sca_mlp(const float* part_sum, const float* part_max, int nparts, PadGeom g, CasaW w, float* s1, float* s2, cudaStream_t st) {
-  sca_mlp_kernel<<<g.B, 768, 0, st>>>(part_sum, part_max, nparts, g, w, s1, s2);
-  HITSIR_CHECK(cudaGetLastError());
+  HITSIR_CHECK(launch_pdl(sca_mlp_kernel, dim3(g.B), dim3(768), 0, st, part_sum, part_max, nparts, g, w, s1, s2));
   return 0;
 }
 int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, const float* cmax, const float* s1, const float* s2, CasaW w, bf16* t,
@@ -960,8 +961,7 @@ int launch_qkv_build(const float* x, PadGeom g, int casa, const float* cavg, con
     if (w.bfrag == nullptr) { set_error("launch_qkv_build: casa B fragments were not packed"); return 1; }
     static unsigned long long configured = 0;
     if (ensure_dynamic_smem(qkv_casa_mma_kernel, kMmaSmem, &configured)) return 1;
-    qkv_casa_mma_kernel<<<g.B * g.Hp, 128, kMmaSmem, st>>>(x, g, cavg, cmax, s1, s2, w.bfrag, t);
-    HITSIR_CHECK(cudaGetLastError());
+    HITSIR_CHECK(launch_pdl(qkv_casa_mma_kernel, dim3(g.B * g.Hp), dim3(128), kMmaSmem, st, x, g, cavg, cmax, s1, s2, w.bfrag, t));
     return 0;
   }
   const long long total = (long long)g.B * g.Hp * g.Wp * (kCp / 8);

@@ -150,6 +150,7 @@ scc_dense_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
+  pdl_entry();                                           // up to here only the weights-only k-gen image was read
 
   if (warp == 0) {
     if (lane == 0) {
@@ -420,8 +421,7 @@ int launch_lt(const CUtensorMap& tm_t, const CUtensorMap& tm_o, const Params& p,
   static unsigned long long configured = 0;
   if (ensure_dynamic_smem(scc_dense_kernel<LT>, kSmemBytes, &configured)) return 1;
   const int grid = p.ntiles < num_sms ? p.ntiles : num_sms;
-  scc_dense_kernel<LT><<<grid, 384, kSmemBytes, st>>>(tm_t, tm_o, p);
-  HITSIR_CHECK(cudaGetLastError());
+  HITSIR_CHECK(launch_pdl(scc_dense_kernel<LT>, dim3(grid), dim3(384), kSmemBytes, st, tm_t, tm_o, p));
   return 0;
 }
 

@@ -184,6 +184,7 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
   const int mult = p.streaming ? 2 : 1;
+  pdl_entry();                                           // up to here only the weights-only k-gen image was read
 
   if (warp == 0) {
     if (lane == 0) {
@@ -625,8 +626,7 @@ int launch_scc_umma(const bf16* t, const SccGeom& g, const SccW& w, bf16* out, f
   if (make_tmap_nhwc(&tm_t, t, g.pg.B, g.pg.Hp, g.pg.Wp, kCp, 64, (uint32_t)tg.bx, (uint32_t)tg.by)) return 1;
   if (make_tmap_nhwc(&tm_o, out, g.pg.B, g.pg.H, g.pg.W, kCp, 64, (uint32_t)tg.bx, (uint32_t)tg.by)) return 1;
   const int grid = p.nwin < num_sms ? p.nwin : num_sms;
-  scc_umma_kernel<<<grid, 384, kSmemBytes, st>>>(tm_t, tm_o, p);
-  HITSIR_CHECK(cudaGetLastError());
+  HITSIR_CHECK(launch_pdl(scc_umma_kernel, dim3(grid), dim3(384), kSmemBytes, st, tm_t, tm_o, p));
   return 0;
 }
 

@@ -140,6 +140,7 @@ umma_gemm_tma_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_entry();                                           // up to here only weights (bias / gamma / beta) were read
 
   if (warp == 0) {
     if (lane == 0) {
@@ -449,8 +450,7 @@ static int launch_tma_bn(const GemmParams& p, const CUtensorMap* maps, int num_s
   q.b_resident = (p.b_resident && !p.conv && grid % p.n_tiles == 0 &&
                   p.num_kb * Cfg::kBBytes + Cfg::kStages * Cfg::kABytes <= Cfg::kPipeBytes) ? 1 : 0;
   if (p.n_tiles * BN > Cfg::kMaxCols) { set_error("launch_umma_gemm_tma: %d output columns exceed the staged-parameter limit %d", p.n_tiles * BN, Cfg::kMaxCols); return 1; }
-  umma_gemm_tma_kernel<BN, EQ><<<grid, 128 + 128 * EQ, Cfg::kSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], q);
-  HITSIR_CHECK(cudaGetLastError());
+  HITSIR_CHECK(launch_pdl(umma_gemm_tma_kernel<BN, EQ>, dim3(grid), dim3(128 + 128 * EQ), Cfg::kSmemBytes, st, maps[0], maps[1], maps[2], maps[3], maps[4], q));
   return 0;
 }
 
