@@ -224,7 +224,10 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
           load_chunk(p.pool_img + (size_t)t * p.pool_bytes, (uint32_t)p.pool_bytes);
         }
         wait_bar(mid4_ready, (uint32_t)(wi & 1));      // ring slots double as G / KP operand storage until then
-        for (int t = 0; t < p.tiles; ++t) {
+        for (int tb = 0; tb < p.tiles; ++tb) {
+          // streamed windows walk phase B backwards: the tiles phase A read last are the ones most likely to be in L2 still (148 CTAs x
+          // 18-32 tiles x 48 KB is more than the 126 MB L2, re-reading in the same order missed on every tile)
+          const int t = p.streaming ? p.tiles - 1 - tb : tb;
           if (p.streaming) {
             const int x0 = wx * p.w + (t % p.tiles_x) * p.bx, y0 = wy * p.w + (t / p.tiles_x) * p.by;
             load_tokens(b, x0, y0);
@@ -363,11 +366,12 @@ scc_umma_kernel(const __grid_constant__ CUtensorMap tm_t, const __grid_constant_
       for (int win = blockIdx.x; win < p.nwin; win += gridDim.x) {
         const int wx = win % p.nWx; const int t2 = win / p.nWx; const int wy = t2 % p.nWy; const int b = t2 / p.nWy;
         const uint32_t a0 = tok_cnt;
-        for (int t = 0; t < p.tiles; ++t) {
-          const uint32_t idx = p.streaming ? a0 + (uint32_t)(p.tiles + t) : a0 + (uint32_t)t;
+        for (int tb = 0; tb < p.tiles; ++tb) {
+          const uint32_t idx = p.streaming ? a0 + (uint32_t)(p.tiles + tb) : a0 + (uint32_t)tb;
           const int s = (int)(idx & 1u);
           wait_bar(st_ready(s), st_cnt[s] & 1u);
           ++st_cnt[s];
+          const int t = p.streaming ? p.tiles - 1 - tb : tb;      // phase-B order of the producer
           const int x0 = wx * p.w + (t % p.tiles_x) * p.bx, y0 = wy * p.w + (t / p.tiles_x) * p.by;
           if (x0 < p.W && y0 < p.H) {                 // tiles entirely inside the reflect padding are cropped (:696)
 #pragma unroll
